@@ -1,0 +1,268 @@
+#!/usr/bin/env python3
+"""bench.py -- flow records/s through EWMA throughput-anomaly detection (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one complete TAD job (stage A filter/reduce, group, time sort, stddev_samp, EWMA,
+anomaly compaction) over one synthetic flow table of BASELINE.json configs[1]: 100M records /
+1M connections x 100 points per GPU (weak scaling: every rank holds that many rows of a table
+whose connections are spread over all ranks).
+
+ours:       `value`  = rows / device time per step, inputs resident in HBM (CUDA events recorded by
+                       the library on its own stream: first kernel start -> last kernel end).
+            `e2e`    = same job through the C ABI with HOST (pinned) column buffers: H2D of the
+                       29 B/row inputs and D2H of the result rows inside the timed region.
+reference:  the CPU oracle port (oracle/tad_oracle.c, the restated reference job; the reference
+            itself is PySpark and cannot run in this image) on all host cores, bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "flow records/sec through EWMA anomaly detection"
+BYTES_PER_ROW = 29          # src_ip4 dst_ip4 src_port2 dst_port2 proto1 flow_start4 flow_end4 value8
+RESULT_ROW_BYTES = 46
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.samples, self.stop_flag, self.th = index, [], False, None
+
+    def _run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 6:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def start(self):
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+
+    def stop(self):
+        self.stop_flag = True
+        if self.th:
+            self.th.join(timeout=6)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": int(self.samples[0][1]) if self.samples[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def run_reference(args):
+    """CPU arm: the oracle port with all host threads on a bounded sample of the same workload."""
+    import numpy as np
+    from oracle import c_oracle
+    from theia_b200 import synth
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    series = args.ref_series
+    t = synth.make_flows(series, args.points, seed=1)
+    rows = len(t["value"])
+    c_oracle.build()
+    for _ in range(args.warmup):
+        c_oracle.run_job(t, algo=0, threads=cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cols, ns, npts = c_oracle.run_job(t, algo=0, threads=cores)
+    dt = (time.perf_counter() - t0) / args.steps
+    v = rows / dt
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "records/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "EWMA, %d connections x %d points (sample of 100M records / 1M connections)" % (series, args.points),
+                   "rows_per_step": rows},
+        "cpu_baseline": {"value": v, "unit": "records/s", "cores": cores, "kind": "port",
+                         "sample": "%d rows per step, oracle/tad_oracle.c with OpenMP on %d threads" % (rows, cores)},
+        "e2e": {"value": v, "unit": "records/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    from theia_b200 import synth
+    from theia_b200.engine import DeviceColumns, TadEngine
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    uid = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+        buf = [TadEngine.get_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(buf, src=0)
+        uid = buf[0]
+    eng = TadEngine(device=local, world_size=world, rank=rank, nccl_unique_id=uid)
+
+    S, n = args.series, args.points
+    cols_t = synth.make_flows_torch(S, n, seed=1 + rank, device=dev) if world == 1 else \
+        synth.make_flows_torch_sharded(S, n, seed=1, device=dev, rank=rank, world=world)
+    rows = int(cols_t["value"].numel())
+    torch.cuda.synchronize()
+    dcols = DeviceColumns(rows, {k: v.data_ptr() for k, v in cols_t.items()})
+    dcols.keepalive = cols_t
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(cols):
+        job = eng.submit(cols, algo="EWMA", tad_id="bench")
+        st = job.wait()
+        return job, st
+
+    # ---- value: inputs resident in HBM ---------------------------------------------------------
+    for _ in range(args.warmup):
+        job, st = step(dcols)
+        job.release()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    dev_ms, phase, launches, result_rows = 0.0, {}, 0, 0
+    for _ in range(args.steps):
+        job, st = step(dcols)
+        dev_ms += st["device_ms"]
+        launches += st["gpu_launches"]
+        result_rows = st["result_rows"]
+        for k, v in st["phase_ms"].items():
+            phase[k] = phase.get(k, 0.0) + v
+        job.release()
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    clocks = sampler.stop() if rank == 0 else None
+    stats = torch.tensor([dev_ms / args.steps, wall_ms / args.steps], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+    ms_dev, ms_wall = float(stats[0]), float(stats[1])
+    total_rows = rows * world
+
+    # ---- e2e: host (pinned) buffers through the C ABI, H2D + D2H inside the timed region --------
+    hcols = eng.alloc_columns(rows)
+    for name, tns in cols_t.items():
+        hv = hcols.view(name)
+        hv[:rows] = tns.cpu().numpy().view(hv.dtype)
+    hcols.c.rows = rows
+    for _ in range(max(1, args.warmup // 2)):
+        job, st = step(hcols)
+        job.result(copy=False)
+        job.release()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, args.steps // 2)
+    for _ in range(e2e_steps):
+        job, st = step(hcols)
+        res = job.result(copy=False)
+        d2h = int(st["result_rows"]) * RESULT_ROW_BYTES
+        h2d_ms = st["phase_ms"]["h2d"]
+        job.release()
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    e2e_t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(e2e_t[0])
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        per = {k: v / args.steps for k, v in phase.items()}
+        kern = {k: per[k] for k in ("hist", "scatter", "group", "detect") if per.get(k, 0) > 0}
+        dom = max(kern, key=kern.get)
+        alg_bytes = {"hist": 17, "scatter": 29, "group": 29, "detect": 29}[dom] * rows
+        achieved = alg_bytes / (kern[dom] * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": total_rows / (ms_dev * 1e-3), "unit": "records/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "EWMA, %d records / %d connections x %d points per GPU (BASELINE configs[1])" % (rows, S, n),
+                       "rows_per_gpu": rows, "l2": "inputs (%.1f GB) larger than L2" % (rows * BYTES_PER_ROW / 1e9),
+                       "timing": "library CUDA events on its stream; wall clock per step %.3f ms" % ms_wall},
+            "e2e": {"value": total_rows / (e2e_ms * 1e-3), "unit": "records/s",
+                    "h2d_bytes_per_step": rows * BYTES_PER_ROW, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms, "h2d_ms": h2d_ms},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "pipeline_frac": rows * BYTES_PER_ROW / (ms_dev * 1e-3) / 1e9 / peak},
+            "phase_ms": per, "result_rows": result_rows, "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu:
+            from oracle import c_oracle
+            cores = os.cpu_count() or 1
+            t = synth.make_flows(args.ref_series, n, seed=1)
+            c_oracle.build()
+            c_oracle.run_job(t, algo=0, threads=cores)
+            t0 = time.perf_counter()
+            reps = 3
+            for _ in range(reps):
+                c_oracle.run_job(t, algo=0, threads=cores)
+            dt = (time.perf_counter() - t0) / reps
+            line["cpu_baseline"] = {"value": len(t["value"]) / dt, "unit": "records/s", "cores": cores, "kind": "port",
+                                    "sample": "%d rows x %d reps, oracle/tad_oracle.c OpenMP" % (len(t["value"]), reps)}
+        print(json.dumps(line))
+    hcols.free()
+    eng.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--series", type=int, default=1_000_000)
+    ap.add_argument("--points", type=int, default=100)
+    ap.add_argument("--ref-series", type=int, default=100_000, help="connections in the CPU sample")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

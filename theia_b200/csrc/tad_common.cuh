@@ -1,0 +1,85 @@
+// Shared definitions of the TAD engine kernels (sm_100a).
+//
+// Data layout in HBM:
+//   input    : structure-of-arrays flow columns (tad_columns), 29 B/row for the full key
+//   part[]   : hash-partitioned rows, 32 B each (Row32) = exactly one DRAM sector, so a
+//              fully random scatter has no write amplification
+//   csr_v/t  : per-series, time-sorted, duplicate-reduced values (u64) / flowEndSeconds (u32)
+//   entries  : one 32 B SeriesEntry per connection, written IN PLACE over the dead part[]
+//              region of its bucket (a bucket is fully staged in shared memory before its
+//              entries are written)
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace tad {
+
+struct __align__(32) Row32 {
+    uint64_t a;       // src_ip << 32 | dst_ip
+    uint64_t b;       // flow_start << 32 | src_port << 16 | dst_port
+    uint64_t value;   // throughput
+    uint32_t t;       // flow_end
+    uint32_t proto;
+};
+static_assert(sizeof(Row32) == 32, "Row32 must be one 32-byte sector");
+
+struct __align__(32) SeriesEntry {
+    uint64_t a, b;
+    uint32_t proto;
+    uint32_t n;       // points after the stage-A reduce
+    uint32_t off;     // first point in csr_v / csr_t
+    uint32_t pad;
+};
+static_assert(sizeof(SeriesEntry) == 32, "SeriesEntry aliases a Row32 slot");
+
+struct ColPtrs {
+    const uint32_t *src_ip, *dst_ip, *flow_start, *flow_end;
+    const uint16_t *src_port, *dst_port;
+    const uint8_t *proto;
+    const uint64_t *value;
+    const uint32_t *src_ns, *dst_ns;
+};
+
+struct RowFilter {
+    uint32_t start_time, end_time;   // 0 = unbounded
+    uint32_t n_ns_ignore;
+    const uint32_t *ns_ignore;       // device pointer
+};
+
+struct OutCols {
+    uint32_t *src_ip, *dst_ip, *flow_start, *flow_end;
+    uint16_t *src_port, *dst_port;
+    uint8_t *proto, *anomaly;
+    double *stddev, *algo_calc, *throughput;
+};
+
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t x)
+{
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
+    return x;
+}
+
+// 64-bit hash of the 136-bit connection key.  Top bits select the bucket (and, across
+// GPUs, the owner rank); the next bits select the shared-memory hash-table slot.
+__host__ __device__ __forceinline__ uint64_t key_hash(uint64_t a, uint64_t b, uint32_t proto)
+{
+    return mix64(a ^ mix64(b + 0x9e3779b97f4a7c15ULL * (uint64_t)(proto + 1u)));
+}
+
+// device scalars the host reads back between phases
+enum {
+    ST_KEPT = 0,        // rows that passed the stage-A filters
+    ST_NBIG,            // buckets larger than the shared-memory capacity
+    ST_BIGROWS,         // rows in those buckets
+    ST_MAXBUCKET,
+    ST_SERIES,          // total series
+    ST_POINTS,          // total points after the reduce
+    ST_OUTCOUNT,        // result rows produced (may exceed capacity -> rerun)
+    ST_COUNT
+};
+
+constexpr int kGroupCap = 2048;       // rows a bucket may hold to take the shared-memory path
+constexpr int kGroupThreads = 256;
+constexpr int kGroupHT = 2 * kGroupCap;
+
+}  // namespace tad

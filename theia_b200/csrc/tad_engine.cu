@@ -1,0 +1,714 @@
+// Host side of the TAD engine: C ABI (include/theia_tad.h), job queue, workspace, phase
+// orchestration.  One worker thread per context runs jobs FIFO on one CUDA stream; callers
+// (the controller's workers, pkg/controller/util.go:43) only enqueue and poll.
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include "../../include/theia_tad.h"
+#include "tad_kernels.h"
+#include "tad_nccl.h"
+
+using namespace tad;
+
+namespace {
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+struct PinnedBlock {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+constexpr int kMaxEvents = 24;
+constexpr int kTotalStages = 6;   // ingest, partition, exchange, group, detect, egress
+
+double now_ms()
+{
+    using namespace std::chrono;
+    return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+}  // namespace
+
+struct tad_job {
+    tad_ctx *ctx = nullptr;
+    tad_job_spec spec{};
+    std::vector<uint32_t> ns_ignore;
+    tad_columns cols{};
+    std::mutex mu;
+    std::condition_variable cv;
+    tad_status st{};
+    std::atomic<int> cancel{0};
+    PinnedBlock result_block;
+    tad_rows rows{};
+    double t_submit = 0;
+};
+
+struct tad_ctx {
+    tad_config cfg{};
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[kMaxEvents]{};
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<tad_job *> queue;
+    std::thread worker;
+    bool stop = false;
+    int debug_logb = -1;
+    int num_sms = 148;
+    // device workspace (grow-only, reused across jobs; jobs are serialized by the worker)
+    DevBuf d_col[10], hist, offsets, cursor, big_list, stats, part, csr_v, csr_t, nsb, npb, sbase, outb, ns_ignore, spill,
+        dbx, dbi, exch;
+    uint32_t *h_stats = nullptr;   // pinned readback of the device scalars
+    std::mutex pool_mu;
+    std::vector<PinnedBlock> pinned_pool;
+    NcclComm nccl;
+};
+
+namespace {
+
+const char *kErrNames[] = {"ok", "invalid argument", "CUDA error", "out of memory", "NCCL error", "illegal state",
+                           "cancelled", "unsupported", "internal error"};
+
+struct JobFail {
+    int code;
+    char msg[256];
+};
+
+[[noreturn]] void fail(int code, const char *fmt, ...)
+{
+    JobFail f;
+    f.code = code;
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(f.msg, sizeof(f.msg), fmt, ap);
+    va_end(ap);
+    throw f;
+}
+
+#define CU(expr)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess)                                                                           \
+            fail(_e == cudaErrorMemoryAllocation ? TAD_ERR_NOMEM : TAD_ERR_CUDA, "%s: %s (%s:%d)", #expr, \
+                 cudaGetErrorString(_e), __FILE__, __LINE__);                                            \
+    } while (0)
+
+void ensure(DevBuf &b, size_t bytes)
+{
+    if (bytes <= b.cap) return;
+    if (b.p) CU(cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+    size_t want = bytes + bytes / 16 + 256;
+    want = (want + 255) & ~size_t(255);
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        want = (bytes + 255) & ~size_t(255);
+        CU(cudaMalloc(&b.p, want));
+    }
+    b.cap = want;
+}
+
+PinnedBlock take_pinned(tad_ctx *ctx, size_t bytes)
+{
+    {
+        std::lock_guard<std::mutex> lk(ctx->pool_mu);
+        int best = -1;
+        for (size_t i = 0; i < ctx->pinned_pool.size(); i++)
+            if (ctx->pinned_pool[i].cap >= bytes && (best < 0 || ctx->pinned_pool[i].cap < ctx->pinned_pool[best].cap))
+                best = (int)i;
+        if (best >= 0) {
+            PinnedBlock b = ctx->pinned_pool[best];
+            ctx->pinned_pool.erase(ctx->pinned_pool.begin() + best);
+            return b;
+        }
+    }
+    PinnedBlock b;
+    b.cap = (bytes + bytes / 8 + 4095) & ~size_t(4095);
+    CU(cudaHostAlloc(&b.p, b.cap, cudaHostAllocDefault));
+    return b;
+}
+
+void give_pinned(tad_ctx *ctx, PinnedBlock b)
+{
+    if (!b.p) return;
+    std::lock_guard<std::mutex> lk(ctx->pool_mu);
+    ctx->pinned_pool.push_back(b);
+}
+
+void set_progress(tad_job *job, int state, int completed)
+{
+    std::lock_guard<std::mutex> lk(job->mu);
+    job->st.state = state;
+    job->st.completed_stages = completed;
+}
+
+int pick_logb(const tad_ctx *ctx, uint64_t rows)
+{
+    if (ctx->debug_logb >= 0) return ctx->debug_logb;
+    // mean bucket ~ 0.375 * capacity: connection sizes are lumpy, so leave head-room
+    const uint64_t target = (uint64_t)(kGroupCap * 3 / 8);
+    int logb = 0;
+    while (logb < 22 && (rows >> logb) > target) logb++;
+    return logb;
+}
+
+size_t col_bytes(int idx, uint64_t rows)
+{
+    static const size_t w[10] = {4, 4, 2, 2, 1, 4, 4, 8, 4, 4};
+    return w[idx] * rows;
+}
+
+void *col_ptr(const tad_columns &c, int idx)
+{
+    switch (idx) {
+    case 0: return c.src_ip;
+    case 1: return c.dst_ip;
+    case 2: return c.src_port;
+    case 3: return c.dst_port;
+    case 4: return c.proto;
+    case 5: return c.flow_start;
+    case 6: return c.flow_end;
+    case 7: return c.value;
+    case 8: return c.src_ns;
+    default: return c.dst_ns;
+    }
+}
+
+struct OutLayout {
+    size_t off[11];
+    size_t total;
+};
+// src_ip dst_ip flow_start flow_end (u32) | stddev algo_calc throughput (f64) | ports (u16) | proto anomaly (u8)
+OutLayout out_layout(uint64_t cap)
+{
+    OutLayout L;
+    size_t o = 0;
+    auto add = [&](int i, size_t w) {
+        L.off[i] = o;
+        o += (w * cap + 255) & ~size_t(255);
+    };
+    add(0, 8); add(1, 8); add(2, 8);          // stddev, algo_calc, throughput
+    add(3, 4); add(4, 4); add(5, 4); add(6, 4);  // src_ip, dst_ip, flow_start, flow_end
+    add(7, 2); add(8, 2);                      // src_port, dst_port
+    add(9, 1); add(10, 1);                     // proto, anomaly
+    L.total = o;
+    return L;
+}
+
+OutCols out_cols(void *base, const OutLayout &L)
+{
+    char *b = static_cast<char *>(base);
+    OutCols o;
+    o.stddev = reinterpret_cast<double *>(b + L.off[0]);
+    o.algo_calc = reinterpret_cast<double *>(b + L.off[1]);
+    o.throughput = reinterpret_cast<double *>(b + L.off[2]);
+    o.src_ip = reinterpret_cast<uint32_t *>(b + L.off[3]);
+    o.dst_ip = reinterpret_cast<uint32_t *>(b + L.off[4]);
+    o.flow_start = reinterpret_cast<uint32_t *>(b + L.off[5]);
+    o.flow_end = reinterpret_cast<uint32_t *>(b + L.off[6]);
+    o.src_port = reinterpret_cast<uint16_t *>(b + L.off[7]);
+    o.dst_port = reinterpret_cast<uint16_t *>(b + L.off[8]);
+    o.proto = reinterpret_cast<uint8_t *>(b + L.off[9]);
+    o.anomaly = reinterpret_cast<uint8_t *>(b + L.off[10]);
+    return o;
+}
+
+void run_job(tad_ctx *ctx, tad_job *job)
+{
+    const tad_job_spec &sp = job->spec;
+    const tad_columns &hc = job->cols;
+    const uint64_t R = hc.rows;
+    cudaStream_t st = ctx->stream;
+    uint64_t launches = 0;
+    int nev = 0;
+    int ev_phase[kMaxEvents];
+    auto mark = [&](int phase) {          // event closing `phase`
+        if (nev < kMaxEvents) {
+            CU(cudaEventRecord(ctx->ev[nev], st));
+            ev_phase[nev++] = phase;
+        }
+    };
+    auto check_cancel = [&]() {
+        if (job->cancel.load()) fail(TAD_ERR_CANCELLED, "job cancelled");
+    };
+
+    CU(cudaSetDevice(ctx->cfg.device));
+    set_progress(job, TAD_STATE_RUNNING, 0);
+    ensure(ctx->stats, 64 * sizeof(uint32_t));
+    uint32_t *d_stats = static_cast<uint32_t *>(ctx->stats.p);
+    CU(cudaMemsetAsync(d_stats, 0, 64 * sizeof(uint32_t), st));
+
+    // ---- ingest: host columns -> device (device-resident columns are used in place) -------
+    ColPtrs c{};
+    const void *dcol[10];
+    mark(-1);
+    for (int i = 0; i < 10; i++) {
+        void *src = col_ptr(hc, i);
+        dcol[i] = nullptr;
+        if (!src || R == 0) continue;
+        if (hc.mem == TAD_MEM_DEVICE) {
+            dcol[i] = src;
+        } else {
+            ensure(ctx->d_col[i], col_bytes(i, R));
+            CU(cudaMemcpyAsync(ctx->d_col[i].p, src, col_bytes(i, R), cudaMemcpyHostToDevice, st));
+            dcol[i] = ctx->d_col[i].p;
+        }
+    }
+    mark(TAD_PHASE_H2D);
+    c.src_ip = (const uint32_t *)dcol[0]; c.dst_ip = (const uint32_t *)dcol[1];
+    c.src_port = (const uint16_t *)dcol[2]; c.dst_port = (const uint16_t *)dcol[3];
+    c.proto = (const uint8_t *)dcol[4]; c.flow_start = (const uint32_t *)dcol[5];
+    c.flow_end = (const uint32_t *)dcol[6]; c.value = (const uint64_t *)dcol[7];
+    c.src_ns = (const uint32_t *)dcol[8]; c.dst_ns = (const uint32_t *)dcol[9];
+
+    RowFilter f{};
+    f.start_time = sp.start_time;
+    f.end_time = sp.end_time;
+    if (!job->ns_ignore.empty() && (c.src_ns || c.dst_ns)) {
+        ensure(ctx->ns_ignore, job->ns_ignore.size() * 4);
+        CU(cudaMemcpyAsync(ctx->ns_ignore.p, job->ns_ignore.data(), job->ns_ignore.size() * 4, cudaMemcpyHostToDevice, st));
+        f.n_ns_ignore = (uint32_t)job->ns_ignore.size();
+        f.ns_ignore = static_cast<const uint32_t *>(ctx->ns_ignore.p);
+    }
+
+    // ---- partition -------------------------------------------------------------------------
+    const int logB = pick_logb(ctx, R);
+    const uint32_t B = 1u << logB;
+    ensure(ctx->hist, (size_t)B * 4);
+    ensure(ctx->offsets, ((size_t)B + 1) * 4);
+    ensure(ctx->cursor, (size_t)B * 4);
+    ensure(ctx->big_list, (size_t)B * 4);
+    ensure(ctx->nsb, (size_t)B * 4);
+    ensure(ctx->npb, (size_t)B * 4);
+    ensure(ctx->sbase, ((size_t)B + 1) * 4);
+    ensure(ctx->part, (R ? R : 1) * sizeof(Row32));
+    ensure(ctx->csr_v, (R ? R : 1) * 8);
+    ensure(ctx->csr_t, (R ? R : 1) * 4);
+    uint32_t *hist = (uint32_t *)ctx->hist.p, *offsets = (uint32_t *)ctx->offsets.p, *cursor = (uint32_t *)ctx->cursor.p;
+    uint32_t *big_list = (uint32_t *)ctx->big_list.p, *nsb = (uint32_t *)ctx->nsb.p, *npb = (uint32_t *)ctx->npb.p;
+    uint32_t *sbase = (uint32_t *)ctx->sbase.p;
+    Row32 *part = (Row32 *)ctx->part.p;
+    uint64_t *csr_v = (uint64_t *)ctx->csr_v.p;
+    uint32_t *csr_t = (uint32_t *)ctx->csr_t.p;
+
+    CU(cudaMemsetAsync(hist, 0, (size_t)B * 4, st));
+    CU(cudaMemsetAsync(nsb, 0, (size_t)B * 4, st));
+    CU(cudaMemsetAsync(npb, 0, (size_t)B * 4, st));
+    mark(-1);
+    CU(launch_hist(st, c, R, f, logB, hist)); launches += R ? 1 : 0;
+    mark(TAD_PHASE_HIST);
+    CU(launch_bucket_scan(st, hist, offsets, cursor, B, kGroupCap, big_list, B, d_stats)); launches++;
+    mark(TAD_PHASE_SCAN);
+    CU(launch_scatter(st, c, R, f, logB, cursor, part)); launches += R ? 1 : 0;
+    mark(TAD_PHASE_SCATTER);
+    CU(cudaMemcpyAsync(ctx->h_stats, d_stats, ST_COUNT * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    check_cancel();
+    const uint64_t kept = ctx->h_stats[ST_KEPT];
+    const uint32_t n_big = ctx->h_stats[ST_NBIG];
+    const uint64_t big_rows = ctx->h_stats[ST_BIGROWS];
+    set_progress(job, TAD_STATE_RUNNING, 3);    // ingest, partition, exchange (single GPU: no-op)
+
+    // ---- group ------------------------------------------------------------------------------
+    mark(-1);
+    CU(launch_group(st, part, offsets, B, logB, csr_v, csr_t, nsb, npb, sp.reducer)); launches++;
+    mark(TAD_PHASE_GROUP);
+    if (n_big) {
+        const size_t need = spill_scratch_bytes(big_rows);
+        ensure(ctx->spill, need);
+        int l = 0;
+        CU(run_spill(st, part, offsets, big_list, n_big, big_rows, ctx->spill.p, ctx->spill.cap, csr_v, csr_t, nsb, npb,
+                     sp.reducer, &l));
+        launches += l;
+        mark(TAD_PHASE_SPILL);
+    }
+    CU(launch_series_scan(st, nsb, npb, sbase, B, d_stats)); launches++;
+    CU(cudaMemcpyAsync(ctx->h_stats, d_stats, ST_COUNT * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    check_cancel();
+    const uint32_t S = ctx->h_stats[ST_SERIES];
+    const uint64_t points = ctx->h_stats[ST_POINTS];
+    set_progress(job, TAD_STATE_RUNNING, 4);
+
+    // ---- detect -----------------------------------------------------------------------------
+    const bool emit_all = (sp.flags & TAD_FLAG_EMIT_ALL) != 0;
+    uint64_t out_cap = emit_all ? points : (points / 8 + (1u << 16));
+    if (out_cap > points) out_cap = points;
+    if (out_cap == 0) out_cap = 1;
+    uint64_t out_rows = 0;
+    OutLayout L{};
+    OutCols oc{};
+    for (int attempt = 0; attempt < 3; attempt++) {
+        L = out_layout(out_cap);
+        ensure(ctx->outb, L.total);
+        oc = out_cols(ctx->outb.p, L);
+        CU(cudaMemsetAsync(d_stats + ST_OUTCOUNT, 0, 4, st));
+        mark(-1);
+        if (sp.algo == TAD_ALGO_EWMA) {
+            CU(launch_detect_ewma(st, part, offsets, sbase, B, S, csr_v, csr_t, oc, (uint32_t)out_cap, d_stats, emit_all));
+            launches += S ? 1 : 0;
+        } else if (sp.algo == TAD_ALGO_DBSCAN) {
+            ensure(ctx->dbx, (points ? points : 1) * 8);
+            ensure(ctx->dbi, (points ? points : 1) * 4);
+            CU(launch_detect_dbscan(st, part, offsets, sbase, B, S, csr_v, csr_t, (double *)ctx->dbx.p, (uint32_t *)ctx->dbi.p,
+                                    oc, (uint32_t)out_cap, d_stats, emit_all));
+            launches += S ? 1 : 0;
+        } else {
+            fail(TAD_ERR_UNSUPPORTED, "algorithm %d is not implemented by this build", sp.algo);
+        }
+        mark(TAD_PHASE_DETECT);
+        CU(cudaMemcpyAsync(ctx->h_stats, d_stats, ST_COUNT * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        out_rows = ctx->h_stats[ST_OUTCOUNT];
+        if (out_rows <= out_cap) break;
+        out_cap = out_rows;                 // capacity guess too small: rerun detect (idempotent)
+        if (attempt == 2) fail(TAD_ERR_INTERNAL, "result capacity did not converge");
+    }
+    check_cancel();
+    set_progress(job, TAD_STATE_RUNNING, 5);
+
+    // ---- egress: result rows -> pinned host memory -------------------------------------------
+    mark(-1);
+    {
+        static const size_t w[11] = {8, 8, 8, 4, 4, 4, 4, 2, 2, 1, 1};
+        OutLayout HL = out_layout(out_rows ? out_rows : 1);
+        job->result_block = take_pinned(ctx, HL.total);
+        char *hb = static_cast<char *>(job->result_block.p);
+        const char *db = static_cast<const char *>(ctx->outb.p);
+        for (int i = 0; i < 11 && out_rows; i++)
+            CU(cudaMemcpyAsync(hb + HL.off[i], db + L.off[i], w[i] * out_rows, cudaMemcpyDeviceToHost, st));
+        OutCols ho = out_cols(hb, HL);
+        job->rows.rows = out_rows;
+        job->rows.src_ip = ho.src_ip; job->rows.dst_ip = ho.dst_ip;
+        job->rows.src_port = ho.src_port; job->rows.dst_port = ho.dst_port;
+        job->rows.proto = ho.proto; job->rows.flow_start = ho.flow_start; job->rows.flow_end = ho.flow_end;
+        job->rows.stddev = ho.stddev; job->rows.algo_calc = ho.algo_calc; job->rows.throughput = ho.throughput;
+        job->rows.anomaly = ho.anomaly;
+    }
+    mark(TAD_PHASE_D2H);
+    CU(cudaStreamSynchronize(st));
+
+    // ---- status ---------------------------------------------------------------------------------
+    double phase_ms[TAD_NPHASES] = {0};
+    float total = 0;
+    for (int i = 1; i < nev; i++) {
+        if (ev_phase[i] < 0) continue;
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, ctx->ev[i - 1], ctx->ev[i]));
+        phase_ms[ev_phase[i]] += ms;
+    }
+    // device span excludes the H2D/D2H copies: first partition event .. last detect event
+    int first_k = -1, last_k = -1;
+    for (int i = 0; i < nev; i++) {
+        if (ev_phase[i] == TAD_PHASE_HIST && first_k < 0) first_k = i - 1;
+        if (ev_phase[i] == TAD_PHASE_DETECT) last_k = i;
+    }
+    if (first_k >= 0 && last_k > first_k) CU(cudaEventElapsedTime(&total, ctx->ev[first_k], ctx->ev[last_k]));
+    {
+        std::lock_guard<std::mutex> lk(job->mu);
+        tad_status &s = job->st;
+        s.rows_in = R;
+        s.rows_kept = kept;
+        s.rows_owned = kept;
+        s.points = points;
+        s.series = S;
+        s.result_rows = out_rows;
+        s.spill_rows = big_rows;
+        s.gpu_launches = launches;
+        s.device_ms = total;
+        for (int i = 0; i < TAD_NPHASES; i++) s.phase_ms[i] = phase_ms[i];
+        s.total_ms = now_ms() - job->t_submit;
+        s.completed_stages = kTotalStages;
+        s.state = TAD_STATE_COMPLETED;
+        job->cv.notify_all();     // last touch of `job` by the worker (tad_release may free it now)
+    }
+}
+
+void worker_main(tad_ctx *ctx)
+{
+    cudaSetDevice(ctx->cfg.device);
+    for (;;) {
+        tad_job *job = nullptr;
+        {
+            std::unique_lock<std::mutex> lk(ctx->mu);
+            ctx->cv.wait(lk, [&] { return ctx->stop || !ctx->queue.empty(); });
+            if (ctx->queue.empty()) return;       // stop requested and drained
+            job = ctx->queue.front();
+            ctx->queue.pop_front();
+        }
+        try {
+            if (job->cancel.load()) fail(TAD_ERR_CANCELLED, "job cancelled");
+            run_job(ctx, job);
+        } catch (const JobFail &f) {
+            cudaGetLastError();
+            std::lock_guard<std::mutex> lk(job->mu);
+            job->st.state = TAD_STATE_FAILED;
+            job->st.error = f.code;
+            snprintf(job->st.err_msg, sizeof(job->st.err_msg), "%s", f.msg);
+            job->st.total_ms = now_ms() - job->t_submit;
+            job->cv.notify_all();
+        }
+    }
+}
+
+int validate(const tad_job_spec *spec, const tad_columns *cols, char *msg, size_t n)
+{
+    if (spec->algo != TAD_ALGO_EWMA && spec->algo != TAD_ALGO_ARIMA && spec->algo != TAD_ALGO_DBSCAN) {
+        // controller.go:527-529
+        snprintf(msg, n, "invalid request: Throughput Anomaly Detector algorithm type should be 'EWMA' or 'ARIMA' or 'DBSCAN'");
+        return TAD_ERR_INVALID_ARG;
+    }
+    if (spec->reducer != TAD_REDUCE_MAX && spec->reducer != TAD_REDUCE_SUM) {
+        snprintf(msg, n, "invalid request: reducer should be max or sum");
+        return TAD_ERR_INVALID_ARG;
+    }
+    if (spec->start_time && spec->end_time && spec->end_time <= spec->start_time) {
+        // controller.go:535-539
+        snprintf(msg, n, "invalid request: EndInterval should be after StartInterval");
+        return TAD_ERR_INVALID_ARG;
+    }
+    if (cols->rows && (!cols->flow_end || !cols->value)) {
+        snprintf(msg, n, "invalid request: flow_end and value columns are required");
+        return TAD_ERR_INVALID_ARG;
+    }
+    if (cols->rows >= (1ull << 32) - 1) {
+        snprintf(msg, n, "invalid request: at most 2^32-2 rows per GPU");
+        return TAD_ERR_INVALID_ARG;
+    }
+    if (cols->mem != TAD_MEM_HOST && cols->mem != TAD_MEM_DEVICE) {
+        snprintf(msg, n, "invalid request: bad column memory kind");
+        return TAD_ERR_INVALID_ARG;
+    }
+    if (spec->n_ns_ignore && !spec->ns_ignore) {
+        snprintf(msg, n, "invalid request: ns_ignore is NULL");
+        return TAD_ERR_INVALID_ARG;
+    }
+    return TAD_OK;
+}
+
+}  // namespace
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+int tad_abi_version(void) { return TAD_ABI_VERSION; }
+
+int tad_get_unique_id(void *out, size_t bytes)
+{
+    if (!out || bytes < 128) return TAD_ERR_INVALID_ARG;
+    return nccl_get_unique_id(out, bytes) == 0 ? TAD_OK : TAD_ERR_NCCL;
+}
+
+const char *tad_strerror(int err)
+{
+    const int i = -err;
+    if (i < 0 || i > 8) return "unknown error";
+    return kErrNames[i];
+}
+
+int tad_init(const tad_config *cfg, tad_ctx **out)
+{
+    if (!cfg || !out) return TAD_ERR_INVALID_ARG;
+    if (cfg->world_size < 1 || cfg->rank < 0 || cfg->rank >= cfg->world_size) return TAD_ERR_INVALID_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        fprintf(stderr, "theia_tad: no CUDA device is available; this library has no CPU fallback\n");
+        return TAD_ERR_CUDA;
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) return TAD_ERR_INVALID_ARG;
+    if (cudaSetDevice(cfg->device) != cudaSuccess) return TAD_ERR_CUDA;
+    tad_ctx *ctx = new tad_ctx();
+    ctx->cfg = *cfg;
+    ctx->cfg.nccl_unique_id = nullptr;
+    if (const char *e = getenv("TAD_DEBUG_LOGB")) ctx->debug_logb = atoi(e);
+    cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, cfg->device);
+    bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; ok && i < kMaxEvents; i++) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
+    ok = ok && cudaHostAlloc((void **)&ctx->h_stats, 64 * sizeof(uint32_t), cudaHostAllocDefault) == cudaSuccess;
+    if (!ok) {
+        delete ctx;
+        return TAD_ERR_CUDA;
+    }
+    if (cfg->world_size > 1) {
+        int rc = nccl_comm_init(&ctx->nccl, cfg->world_size, cfg->rank, cfg->nccl_unique_id, cfg->nccl_unique_id_bytes);
+        if (rc != 0) {
+            delete ctx;
+            return TAD_ERR_NCCL;
+        }
+    }
+    ctx->worker = std::thread(worker_main, ctx);
+    *out = ctx;
+    return TAD_OK;
+}
+
+void tad_shutdown(tad_ctx *ctx)
+{
+    if (!ctx) return;
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        ctx->stop = true;
+    }
+    ctx->cv.notify_all();
+    if (ctx->worker.joinable()) ctx->worker.join();
+    cudaSetDevice(ctx->cfg.device);
+    nccl_comm_destroy(&ctx->nccl);
+    DevBuf *bufs[] = {&ctx->hist, &ctx->offsets, &ctx->cursor, &ctx->big_list, &ctx->stats, &ctx->part, &ctx->csr_v,
+                      &ctx->csr_t, &ctx->nsb, &ctx->npb, &ctx->sbase, &ctx->outb, &ctx->ns_ignore, &ctx->spill, &ctx->dbx,
+                      &ctx->dbi, &ctx->exch};
+    for (DevBuf *b : bufs)
+        if (b->p) cudaFree(b->p);
+    for (int i = 0; i < 10; i++)
+        if (ctx->d_col[i].p) cudaFree(ctx->d_col[i].p);
+    for (auto &b : ctx->pinned_pool) cudaFreeHost(b.p);
+    if (ctx->h_stats) cudaFreeHost(ctx->h_stats);
+    for (int i = 0; i < kMaxEvents; i++)
+        if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int tad_alloc_columns(tad_ctx *ctx, uint64_t capacity, int32_t mem, tad_columns *cols)
+{
+    if (!ctx || !cols || (mem != TAD_MEM_HOST && mem != TAD_MEM_DEVICE)) return TAD_ERR_INVALID_ARG;
+    memset(cols, 0, sizeof(*cols));
+    cols->capacity = capacity;
+    cols->mem = mem;
+    if (cudaSetDevice(ctx->cfg.device) != cudaSuccess) return TAD_ERR_CUDA;
+    void **slots[8] = {(void **)&cols->src_ip, (void **)&cols->dst_ip, (void **)&cols->src_port, (void **)&cols->dst_port,
+                       (void **)&cols->proto, (void **)&cols->flow_start, (void **)&cols->flow_end, (void **)&cols->value};
+    for (int i = 0; i < 8; i++) {
+        const size_t bytes = ((col_bytes(i, capacity ? capacity : 1)) + 255) & ~size_t(255);
+        cudaError_t e = mem == TAD_MEM_HOST ? cudaHostAlloc(slots[i], bytes, cudaHostAllocDefault) : cudaMalloc(slots[i], bytes);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            tad_free_columns(ctx, cols);
+            return TAD_ERR_NOMEM;
+        }
+    }
+    return TAD_OK;
+}
+
+int tad_free_columns(tad_ctx *ctx, tad_columns *cols)
+{
+    if (!ctx || !cols) return TAD_ERR_INVALID_ARG;
+    cudaSetDevice(ctx->cfg.device);
+    for (int i = 0; i < 10; i++) {
+        void *p = col_ptr(*cols, i);
+        if (!p) continue;
+        if (cols->mem == TAD_MEM_HOST) cudaFreeHost(p); else cudaFree(p);
+    }
+    memset(cols, 0, sizeof(*cols));
+    return TAD_OK;
+}
+
+int tad_submit(tad_ctx *ctx, const tad_job_spec *spec, const tad_columns *cols, tad_job **out)
+{
+    if (!ctx || !spec || !cols || !out) return TAD_ERR_INVALID_ARG;
+    tad_job *job = new tad_job();
+    job->ctx = ctx;
+    job->spec = *spec;
+    job->spec.id[sizeof(job->spec.id) - 1] = 0;
+    job->cols = *cols;
+    job->t_submit = now_ms();
+    job->st.total_stages = kTotalStages;
+    *out = job;
+    char msg[256];
+    int rc = validate(spec, cols, msg, sizeof(msg));
+    if (rc != TAD_OK) {
+        // like the controller (controller.go:505-514): illegal arguments are terminal FAILED, never retried
+        job->st.state = TAD_STATE_FAILED;
+        job->st.error = rc;
+        snprintf(job->st.err_msg, sizeof(job->st.err_msg), "error in creating AnomalyDetector: %s", msg);
+        return rc;
+    }
+    if (spec->n_ns_ignore) job->ns_ignore.assign(spec->ns_ignore, spec->ns_ignore + spec->n_ns_ignore);
+    job->spec.ns_ignore = nullptr;
+    job->st.state = TAD_STATE_SCHEDULED;
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        if (ctx->stop) {
+            job->st.state = TAD_STATE_FAILED;
+            job->st.error = TAD_ERR_STATE;
+            snprintf(job->st.err_msg, sizeof(job->st.err_msg), "context is shutting down");
+            return TAD_ERR_STATE;
+        }
+        ctx->queue.push_back(job);
+    }
+    ctx->cv.notify_one();
+    return TAD_OK;
+}
+
+int tad_poll(tad_job *job, tad_status *status)
+{
+    if (!job || !status) return TAD_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(job->mu);
+    *status = job->st;
+    return TAD_OK;
+}
+
+int tad_wait(tad_job *job, int64_t timeout_ms, tad_status *status)
+{
+    if (!job) return TAD_ERR_INVALID_ARG;
+    std::unique_lock<std::mutex> lk(job->mu);
+    auto done = [&] { return job->st.state == TAD_STATE_COMPLETED || job->st.state == TAD_STATE_FAILED; };
+    if (timeout_ms < 0) {
+        while (!done()) job->cv.wait_for(lk, std::chrono::milliseconds(50));
+    } else {
+        const double deadline = now_ms() + (double)timeout_ms;
+        while (!done() && now_ms() < deadline) job->cv.wait_for(lk, std::chrono::milliseconds(1));
+    }
+    if (status) *status = job->st;
+    return TAD_OK;
+}
+
+int tad_result(tad_job *job, tad_rows *rows)
+{
+    if (!job || !rows) return TAD_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(job->mu);
+    if (job->st.state != TAD_STATE_COMPLETED) return TAD_ERR_STATE;
+    *rows = job->rows;
+    return TAD_OK;
+}
+
+int tad_cancel(tad_job *job)
+{
+    if (!job) return TAD_ERR_INVALID_ARG;
+    job->cancel.store(1);
+    return TAD_OK;
+}
+
+int tad_release(tad_job *job)
+{
+    if (!job) return TAD_ERR_INVALID_ARG;
+    {
+        std::unique_lock<std::mutex> lk(job->mu);
+        const int s = job->st.state;
+        if (s == TAD_STATE_SCHEDULED || s == TAD_STATE_RUNNING) {
+            job->cancel.store(1);
+            while (!(job->st.state == TAD_STATE_COMPLETED || job->st.state == TAD_STATE_FAILED))
+                job->cv.wait_for(lk, std::chrono::milliseconds(1));
+        }
+    }
+    give_pinned(job->ctx, job->result_block);
+    delete job;
+    return TAD_OK;
+}
+
+}  // extern "C"

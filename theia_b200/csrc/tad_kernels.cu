@@ -1,0 +1,693 @@
+// Hand-written sm_100a kernels of the TAD engine.  See DESIGN.md for the pipeline:
+//
+//   hist     (K1)  columns -> key pack -> 64-bit hash -> bucket histogram      reads 17-21 B/row
+//   bscan    (K1b) exclusive scan of the histogram, oversized-bucket list
+//   scatter  (K2)  columns -> 32 B packed rows, hash-partitioned               reads 29, writes 32 B/row
+//   group    (K3)  one CTA per bucket: TMA bulk load into shared memory, hash-group by
+//                  key, rank-sort each series by flowEndSeconds, reduce duplicates,
+//                  write per-series arrays + series entries                   reads 32, writes 12 B/row
+//   sscan    (K3b) exclusive scan of series-per-bucket
+//   detect   (K4)  one thread per series: stddev_samp (Welford, sequential FP64),
+//                  EWMA / DBSCAN score + flag, two-pass anomaly compaction    reads 8-12 B/row
+//
+// All FP64 arithmetic on the score path uses explicit round-to-nearest intrinsics in the
+// exact operation order of the reference UDFs (anomaly_detection.py:146-212) so that the
+// results are bit-identical to the CPU oracle (no FMA contraction).
+#include "tad_kernels.h"
+
+#include <cstdio>
+
+namespace tad {
+
+// ----------------------------------------------------------------------------------------
+// small PTX helpers
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 ldg_stream128(const void *p)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint2 ldg_stream64(const void *p)
+{
+    uint2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg128(void *p, uint4 v)
+{
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ uint64_t pack64(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
+
+// ----------------------------------------------------------------------------------------
+// K1 / K2: histogram and scatter share the row loader
+// ----------------------------------------------------------------------------------------
+struct RowRegs {
+    uint64_t a, b, value;
+    uint32_t t, proto;
+    bool keep;
+};
+
+__device__ __forceinline__ bool ns_ignored(const RowFilter &f, uint32_t ns)
+{
+    for (uint32_t i = 0; i < f.n_ns_ignore; i++)
+        if (f.ns_ignore[i] == ns) return true;
+    return false;
+}
+
+__device__ __forceinline__ bool row_keep(const RowFilter &f, const ColPtrs &c, uint64_t i, uint32_t fs, uint32_t fe)
+{
+    bool keep = true;
+    if (f.start_time) keep = keep && (fs >= f.start_time);
+    if (f.end_time) keep = keep && (fe < f.end_time);
+    if (f.n_ns_ignore) {
+        if (c.src_ns) keep = keep && !ns_ignored(f, c.src_ns[i]);
+        if (c.dst_ns) keep = keep && !ns_ignored(f, c.dst_ns[i]);
+    }
+    return keep;
+}
+
+template <bool SCATTER>
+__device__ __forceinline__ void emit_row(const RowRegs &r, int bshift, uint32_t *counters, Row32 *part)
+{
+    if (!r.keep) return;
+    const uint64_t h = key_hash(r.a, r.b, r.proto);
+    const uint32_t bucket = bshift >= 64 ? 0u : (uint32_t)(h >> bshift);
+    if (SCATTER) {
+        const uint32_t pos = atomicAdd(&counters[bucket], 1u);
+        uint4 *dst = reinterpret_cast<uint4 *>(part + pos);
+        stg128(dst, make_uint4((uint32_t)r.a, (uint32_t)(r.a >> 32), (uint32_t)r.b, (uint32_t)(r.b >> 32)));
+        stg128(dst + 1, make_uint4((uint32_t)r.value, (uint32_t)(r.value >> 32), r.t, r.proto));
+    } else {
+        atomicAdd(&counters[bucket], 1u);
+    }
+}
+
+__device__ __forceinline__ void load_row_scalar(const ColPtrs &c, const RowFilter &f, uint64_t i, bool need_tv, RowRegs &r)
+{
+    const uint32_t sip = c.src_ip ? c.src_ip[i] : 0u, dip = c.dst_ip ? c.dst_ip[i] : 0u;
+    const uint32_t sp = c.src_port ? c.src_port[i] : 0u, dp = c.dst_port ? c.dst_port[i] : 0u;
+    const uint32_t fs = c.flow_start ? c.flow_start[i] : 0u;
+    const uint32_t fe = (need_tv || f.end_time) ? c.flow_end[i] : 0u;
+    r.a = pack64(dip, sip);
+    r.b = pack64((sp << 16) | dp, fs);
+    r.proto = c.proto ? c.proto[i] : 0u;
+    r.t = fe;
+    r.value = need_tv ? c.value[i] : 0ull;
+    r.keep = row_keep(f, c, i, fs, fe);
+}
+
+// 8 rows per thread, every column read with 128-bit (64-bit for the u8 column) streaming loads.
+template <bool SCATTER, bool VEC>
+__global__ void __launch_bounds__(256) partition_kernel(ColPtrs c, uint64_t R, RowFilter f, int bshift,
+                                                        uint32_t *__restrict__ counters, Row32 *__restrict__ part)
+{
+    const uint64_t ngroups = (R + 7) / 8;
+    const bool need_end = SCATTER || f.end_time != 0;
+    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups;
+         g += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t base = g * 8;
+        if (VEC && base + 8 <= R) {
+            uint4 z = make_uint4(0, 0, 0, 0);
+            uint4 sip0 = z, sip1 = z, dip0 = z, dip1 = z, fs0 = z, fs1 = z, fe0 = z, fe1 = z, sp = z, dp = z;
+            uint4 v0 = z, v1 = z, v2 = z, v3 = z;
+            uint2 pr = make_uint2(0, 0);
+            if (c.src_ip) { sip0 = ldg_stream128(c.src_ip + base); sip1 = ldg_stream128(c.src_ip + base + 4); }
+            if (c.dst_ip) { dip0 = ldg_stream128(c.dst_ip + base); dip1 = ldg_stream128(c.dst_ip + base + 4); }
+            if (c.flow_start) { fs0 = ldg_stream128(c.flow_start + base); fs1 = ldg_stream128(c.flow_start + base + 4); }
+            if (need_end) { fe0 = ldg_stream128(c.flow_end + base); fe1 = ldg_stream128(c.flow_end + base + 4); }
+            if (c.src_port) sp = ldg_stream128(c.src_port + base);
+            if (c.dst_port) dp = ldg_stream128(c.dst_port + base);
+            if (c.proto) pr = ldg_stream64(c.proto + base);
+            if (SCATTER) {
+                v0 = ldg_stream128(c.value + base); v1 = ldg_stream128(c.value + base + 2);
+                v2 = ldg_stream128(c.value + base + 4); v3 = ldg_stream128(c.value + base + 6);
+            }
+            const uint32_t sipv[8] = {sip0.x, sip0.y, sip0.z, sip0.w, sip1.x, sip1.y, sip1.z, sip1.w};
+            const uint32_t dipv[8] = {dip0.x, dip0.y, dip0.z, dip0.w, dip1.x, dip1.y, dip1.z, dip1.w};
+            const uint32_t fsv[8] = {fs0.x, fs0.y, fs0.z, fs0.w, fs1.x, fs1.y, fs1.z, fs1.w};
+            const uint32_t fev[8] = {fe0.x, fe0.y, fe0.z, fe0.w, fe1.x, fe1.y, fe1.z, fe1.w};
+            const uint32_t spw[4] = {sp.x, sp.y, sp.z, sp.w};
+            const uint32_t dpw[4] = {dp.x, dp.y, dp.z, dp.w};
+            const uint32_t vlo[8] = {v0.x, v0.z, v1.x, v1.z, v2.x, v2.z, v3.x, v3.z};
+            const uint32_t vhi[8] = {v0.y, v0.w, v1.y, v1.w, v2.y, v2.w, v3.y, v3.w};
+            RowRegs r[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const uint32_t sport = (spw[i >> 1] >> (16 * (i & 1))) & 0xffffu;
+                const uint32_t dport = (dpw[i >> 1] >> (16 * (i & 1))) & 0xffffu;
+                const uint32_t pw = i < 4 ? pr.x : pr.y;
+                r[i].a = pack64(dipv[i], sipv[i]);
+                r[i].b = pack64((sport << 16) | dport, fsv[i]);
+                r[i].proto = (pw >> (8 * (i & 3))) & 0xffu;
+                r[i].t = fev[i];
+                r[i].value = pack64(vlo[i], vhi[i]);
+                r[i].keep = row_keep(f, c, base + i, fsv[i], fev[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; i++) emit_row<SCATTER>(r[i], bshift, counters, part);
+        } else {
+            const uint64_t end = base + 8 < R ? base + 8 : R;
+            for (uint64_t i = base; i < end; i++) {
+                RowRegs r;
+                load_row_scalar(c, f, i, SCATTER, r);
+                emit_row<SCATTER>(r, bshift, counters, part);
+            }
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------
+// single-CTA exclusive scans (bucket offsets; series base per bucket)
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t block_exclusive_scan_1024(uint32_t v, uint32_t *total)
+{
+    __shared__ uint32_t warp_sums[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += o;
+    }
+    if (lane == 31) warp_sums[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = warp_sums[lane];
+        uint32_t winc = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t o = __shfl_up_sync(0xffffffffu, winc, d);
+            if (lane >= d) winc += o;
+        }
+        warp_sums[lane] = winc - w;
+        if (lane == 31) *total = winc;
+    }
+    __syncthreads();
+    return warp_sums[warp] + inc - v;
+}
+
+// offsets[B+1] = exclusive scan of hist; cursor = copy of offsets; lists buckets > cap.
+__global__ void __launch_bounds__(1024) bucket_scan_kernel(const uint32_t *__restrict__ hist, uint32_t *__restrict__ offsets,
+                                                           uint32_t *__restrict__ cursor, uint32_t B, uint32_t cap,
+                                                           uint32_t *__restrict__ big_list, uint32_t big_cap,
+                                                           uint32_t *__restrict__ stats)
+{
+    __shared__ uint32_t total_s;
+    __shared__ uint32_t nbig_s, maxb_s;
+    __shared__ unsigned long long bigrows_s;
+    if (threadIdx.x == 0) { nbig_s = 0; maxb_s = 0; bigrows_s = 0; }
+    const uint32_t per = (B + 1023) / 1024;
+    const uint32_t lo = min(B, threadIdx.x * per), hi = min(B, lo + per);
+    uint32_t sum = 0;
+    for (uint32_t i = lo; i < hi; i++) sum += hist[i];
+    const uint32_t pre = block_exclusive_scan_1024(sum, &total_s);
+    uint32_t run = pre, mx = 0;
+    for (uint32_t i = lo; i < hi; i++) {
+        const uint32_t h = hist[i];
+        offsets[i] = run;
+        cursor[i] = run;
+        run += h;
+        mx = max(mx, h);
+        if (h > cap) {
+            const uint32_t k = atomicAdd(&nbig_s, 1u);
+            if (k < big_cap) big_list[k] = i;
+            atomicAdd(&bigrows_s, (unsigned long long)h);
+        }
+    }
+    atomicMax(&maxb_s, mx);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        offsets[B] = total_s;
+        stats[ST_KEPT] = total_s;
+        stats[ST_NBIG] = nbig_s;
+        stats[ST_BIGROWS] = (uint32_t)bigrows_s;
+        stats[ST_MAXBUCKET] = maxb_s;
+    }
+}
+
+// sbase[B+1] = exclusive scan of series-per-bucket; also totals points.
+__global__ void __launch_bounds__(1024) series_scan_kernel(const uint32_t *__restrict__ nsb, const uint32_t *__restrict__ npb,
+                                                           uint32_t *__restrict__ sbase, uint32_t B, uint32_t *__restrict__ stats)
+{
+    __shared__ uint32_t total_s;
+    __shared__ unsigned long long points_s;
+    if (threadIdx.x == 0) points_s = 0;
+    const uint32_t per = (B + 1023) / 1024;
+    const uint32_t lo = min(B, threadIdx.x * per), hi = min(B, lo + per);
+    uint32_t sum = 0;
+    unsigned long long pts = 0;
+    for (uint32_t i = lo; i < hi; i++) { sum += nsb[i]; pts += npb[i]; }
+    const uint32_t pre = block_exclusive_scan_1024(sum, &total_s);
+    uint32_t run = pre;
+    for (uint32_t i = lo; i < hi; i++) { sbase[i] = run; run += nsb[i]; }
+    atomicAdd(&points_s, pts);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        sbase[B] = total_s;
+        stats[ST_SERIES] = total_s;
+        stats[ST_POINTS] = (uint32_t)points_s;
+    }
+}
+
+// ----------------------------------------------------------------------------------------
+// K3: per-bucket group + time sort in shared memory
+// ----------------------------------------------------------------------------------------
+template <int CAP, int NT>
+struct GroupSmem {
+    static constexpr int HT = 2 * CAP;
+    alignas(128) unsigned char x[32 * CAP];   // rows (TMA destination); later ts | tout | vout
+    uint32_t ht[HT];                          // claim: low16 = rep row + 1, high16 = count; later (count << 16) | series idx
+    uint16_t soff[HT];                        // first point of the slot's series inside the bucket
+    alignas(8) unsigned long long mbar;
+    uint32_t warp_sums[32];
+    uint32_t total;
+};
+
+template <int NT>
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *warp_sums, uint32_t *total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int NW = NT / 32;
+    uint32_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += o;
+    }
+    if (lane == 31) warp_sums[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = lane < NW ? warp_sums[lane] : 0u;
+        uint32_t winc = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t o = __shfl_up_sync(0xffffffffu, winc, d);
+            if (lane >= d) winc += o;
+        }
+        if (lane < NW) warp_sums[lane] = winc - w;
+        if (lane == NW - 1) *total = winc;
+    }
+    __syncthreads();
+    return warp_sums[warp] + inc - v;
+}
+
+template <int CAP, int NT>
+__global__ void __launch_bounds__(NT) group_kernel(Row32 *__restrict__ part, const uint32_t *__restrict__ offsets, int sshift,
+                                                   uint64_t *__restrict__ csr_v, uint32_t *__restrict__ csr_t,
+                                                   uint32_t *__restrict__ nsb, uint32_t *__restrict__ npb, int reducer)
+{
+    using S = GroupSmem<CAP, NT>;
+    constexpr int HT = S::HT;
+    constexpr int RPT = CAP / NT;      // rows per thread
+    constexpr int SPT = HT / NT;       // hash slots per thread
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    S &s = *reinterpret_cast<S *>(smem_raw);
+
+    const uint32_t bkt = blockIdx.x;
+    const uint32_t off_b = offsets[bkt];
+    const uint32_t n = offsets[bkt + 1] - off_b;
+    const int tid = threadIdx.x;
+    if (n == 0 || n > (uint32_t)CAP) {          // empty, or oversized -> spill path owns it
+        if (tid == 0 && n == 0) { nsb[bkt] = 0; npb[bkt] = 0; }
+        return;
+    }
+
+    // ---- L: one TMA bulk copy of the whole bucket into shared memory -----------------
+    const uint32_t bar = smem_u32(&s.mbar);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const uint32_t bytes = n * 32u;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     :: "r"(smem_u32(s.x)), "l"(part + off_b), "r"(bytes), "r"(bar) : "memory");
+    }
+#pragma unroll
+    for (int i = 0; i < SPT; i++) s.ht[tid + i * NT] = 0u;
+    __syncthreads();
+    {
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(bar), "r"(0) : "memory");
+        }
+    }
+
+    // ---- G: hash-group rows by key (open addressing, linear probing) -------------------
+    const uint4 *x4 = reinterpret_cast<const uint4 *>(s.x);
+    uint32_t myT[RPT], mySP[RPT];
+    uint64_t myV[RPT];
+#pragma unroll
+    for (int j = 0; j < RPT; j++) {
+        const uint32_t r = tid + j * NT;
+        myT[j] = 0; myV[j] = 0; mySP[j] = 0;
+        if (r < n) {
+            const uint4 k = x4[2 * r], w = x4[2 * r + 1];
+            const uint64_t a = pack64(k.x, k.y), b = pack64(k.z, k.w);
+            const uint32_t proto = w.w;
+            myT[j] = w.z;
+            myV[j] = pack64(w.x, w.y);
+            uint32_t slot = (uint32_t)(key_hash(a, b, proto) >> sshift) & (HT - 1);
+            while (true) {
+                uint32_t cur = *reinterpret_cast<volatile uint32_t *>(&s.ht[slot]);
+                if ((cur & 0xffffu) == 0u) {
+                    const uint32_t old = atomicCAS(&s.ht[slot], 0u, r + 1u);
+                    if (old == 0u) break;
+                    cur = old;
+                }
+                const uint32_t rep = (cur & 0xffffu) - 1u;
+                const uint4 kk = x4[2 * rep];
+                const uint32_t pp = x4[2 * rep + 1].w;
+                if (kk.x == k.x && kk.y == k.y && kk.z == k.z && kk.w == k.w && pp == proto) break;
+                slot = (slot + 1) & (HT - 1);
+            }
+            const uint32_t pos = atomicAdd(&s.ht[slot], 0x10000u) >> 16;
+            mySP[j] = slot | (pos << 16);
+        }
+    }
+    __syncthreads();
+
+    // ---- S: scan slot counts -> series offsets and dense series indices -----------------
+    {
+        const uint32_t base = tid * SPT;
+        uint32_t loc[SPT];
+        uint32_t sum = 0;
+#pragma unroll
+        for (int i = 0; i < SPT; i++) {
+            const uint32_t w = s.ht[base + i];
+            loc[i] = sum;
+            sum += (w >> 16) | ((w & 0xffffu) ? 0x10000u : 0u);     // low16: points, high16: series
+        }
+        const uint32_t pre = block_exclusive_scan<NT>(sum, s.warp_sums, &s.total);
+        SeriesEntry *ent = reinterpret_cast<SeriesEntry *>(part + off_b);
+#pragma unroll
+        for (int i = 0; i < SPT; i++) {
+            const uint32_t w = s.ht[base + i];
+            if (w & 0xffffu) {
+                const uint32_t ex = pre + loc[i];
+                const uint32_t so = ex & 0xffffu, k = ex >> 16, cnt = w >> 16, rep = (w & 0xffffu) - 1u;
+                const uint4 kk = x4[2 * rep];
+                const uint32_t pp = x4[2 * rep + 1].w;
+                s.soff[base + i] = (uint16_t)so;
+                s.ht[base + i] = (cnt << 16) | k;
+                // series entry, in place over the (already staged) bucket rows
+                uint4 *e4 = reinterpret_cast<uint4 *>(ent + k);
+                e4[0] = kk;
+                e4[1] = make_uint4(pp, cnt, off_b + so, 0u);
+            }
+        }
+    }
+    __syncthreads();                       // rows in s.x are dead from here on
+    const uint32_t ns = s.total >> 16;
+
+    uint32_t *ts = reinterpret_cast<uint32_t *>(s.x);
+    uint32_t *tout = ts + CAP;
+    unsigned long long *vout = reinterpret_cast<unsigned long long *>(s.x + 8 * CAP);
+
+#pragma unroll
+    for (int j = 0; j < RPT; j++) {
+        const uint32_t r = tid + j * NT;
+        if (r < n) {
+            const uint32_t slot = mySP[j] & 0xffffu, pos = mySP[j] >> 16;
+            ts[s.soff[slot] + pos] = myT[j];
+        }
+    }
+    __syncthreads();
+
+    // ---- R: rank every row inside its series by (time, arrival) and place it ------------
+    uint32_t anydup = 0;
+#pragma unroll
+    for (int j = 0; j < RPT; j++) {
+        const uint32_t r = tid + j * NT;
+        if (r < n) {
+            const uint32_t slot = mySP[j] & 0xffffu, pos = mySP[j] >> 16;
+            const uint32_t so = s.soff[slot], cnt = s.ht[slot] >> 16;
+            const uint32_t t = myT[j];
+            uint32_t rank = 0;
+            const uint32_t *tsr = ts + so;
+#pragma unroll 4
+            for (uint32_t q = 0; q < cnt; q++) {
+                const uint32_t tq = tsr[q];
+                rank += (tq < t || (tq == t && q < pos)) ? 1u : 0u;
+            }
+            tout[so + rank] = t;
+            vout[so + rank] = myV[j];
+            mySP[j] = (so + rank) | ((rank ? 1u : 0u) << 31);
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < RPT; j++) {
+        const uint32_t r = tid + j * NT;
+        if (r < n && (mySP[j] >> 31)) {
+            const uint32_t p = mySP[j] & 0x7fffffffu;
+            anydup |= (tout[p - 1] == myT[j]) ? 1u : 0u;
+        }
+    }
+    uint32_t points = n;
+    if (__syncthreads_or((int)anydup)) {
+        // ---- D: rare -- reduce duplicates of (key, flowEndSeconds), one thread per slot ----
+        SeriesEntry *ent = reinterpret_cast<SeriesEntry *>(part + off_b);
+        uint32_t removed = 0;
+        for (int i = 0; i < SPT; i++) {
+            const uint32_t sl = tid * SPT + i;
+            const uint32_t w = s.ht[sl];
+            const uint32_t cnt = w >> 16;
+            if (cnt < 2) continue;
+            const uint32_t so = s.soff[sl];
+            uint32_t wr = 0;
+            for (uint32_t q = 1; q < cnt; q++) {
+                if (tout[so + q] == tout[so + wr]) {
+                    const unsigned long long x = vout[so + wr], y = vout[so + q];
+                    vout[so + wr] = reducer == 0 ? (x > y ? x : y) : (x + y);
+                } else {
+                    ++wr;
+                    tout[so + wr] = tout[so + q];
+                    vout[so + wr] = vout[so + q];
+                }
+            }
+            if (wr + 1 != cnt) {
+                removed += cnt - (wr + 1);
+                ent[w & 0xffffu].n = wr + 1;
+            }
+        }
+        __syncthreads();
+        const uint32_t pre = block_exclusive_scan<NT>(removed, s.warp_sums, &s.total);
+        (void)pre;
+        points = n - s.total;
+    }
+
+    // ---- W: coalesced write of the per-series arrays ------------------------------------
+    for (uint32_t p = tid; p < n; p += NT) {
+        csr_t[off_b + p] = tout[p];
+        csr_v[off_b + p] = vout[p];
+    }
+    if (tid == 0) { nsb[bkt] = ns; npb[bkt] = points; }
+}
+
+// ----------------------------------------------------------------------------------------
+// K4: detect -- one thread per series
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t find_bucket(const uint32_t *__restrict__ sbase, uint32_t B, uint32_t i)
+{
+    // largest b in [0, B) with sbase[b] <= i  (sbase is non-decreasing, sbase[B] = S > i)
+    uint32_t lo = 0, hi = B;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (sbase[mid] <= i) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ void write_out(const OutCols &o, uint32_t idx, const SeriesEntry &e, uint32_t t, double sd,
+                                          double calc, double x, bool flag)
+{
+    o.src_ip[idx] = (uint32_t)(e.a >> 32);
+    o.dst_ip[idx] = (uint32_t)e.a;
+    o.flow_start[idx] = (uint32_t)(e.b >> 32);
+    o.src_port[idx] = (uint16_t)(e.b >> 16);
+    o.dst_port[idx] = (uint16_t)e.b;
+    o.proto[idx] = (uint8_t)e.proto;
+    o.flow_end[idx] = t;
+    o.stddev[idx] = sd;
+    o.algo_calc[idx] = calc;
+    o.throughput[idx] = x;
+    o.anomaly[idx] = flag ? 1 : 0;
+}
+
+// stddev_samp as Spark's CentralMomentAgg computes it (Welford), sequential in time order.
+__device__ __forceinline__ double series_stddev(const uint64_t *__restrict__ v, uint32_t n, bool &has_sd)
+{
+    double cnt = 0.0, avg = 0.0, m2 = 0.0;
+#pragma unroll 4
+    for (uint32_t i = 0; i < n; i++) {
+        const double x = __ull2double_rn(v[i]);
+        cnt = __dadd_rn(cnt, 1.0);
+        const double d = __dsub_rn(x, avg);
+        const double dn = __ddiv_rn(d, cnt);
+        avg = __dadd_rn(avg, dn);
+        m2 = __dadd_rn(m2, __dmul_rn(d, __dsub_rn(d, dn)));
+    }
+    has_sd = n >= 2;
+    return has_sd ? __dsqrt_rn(__ddiv_rn(m2, __dsub_rn(cnt, 1.0))) : __longlong_as_double(0x7ff8000000000000LL);
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT) detect_ewma_kernel(const Row32 *__restrict__ part, const uint32_t *__restrict__ offsets,
+                                                         const uint32_t *__restrict__ sbase, uint32_t B, uint32_t S,
+                                                         const uint64_t *__restrict__ csr_v, const uint32_t *__restrict__ csr_t,
+                                                         OutCols out, uint32_t out_cap, uint32_t *__restrict__ stats, int emit_all)
+{
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t total_s, base_s;
+    const uint32_t i = blockIdx.x * NT + threadIdx.x;
+    SeriesEntry e;
+    e.n = 0;
+    const uint64_t *v = nullptr;
+    bool has_sd = false;
+    double sd = 0.0;
+    uint32_t count = 0;
+    if (i < S) {
+        const uint32_t b = find_bucket(sbase, B, i);
+        const uint4 *p = reinterpret_cast<const uint4 *>(part + offsets[b] + (i - sbase[b]));
+        const uint4 k = p[0], w = p[1];
+        e.a = pack64(k.x, k.y); e.b = pack64(k.z, k.w); e.proto = w.x; e.n = w.y; e.off = w.z;
+        v = csr_v + e.off;
+        sd = series_stddev(v, e.n, has_sd);
+        if (emit_all) {
+            count = e.n;
+        } else if (has_sd) {
+            double prev = 0.0;
+#pragma unroll 4
+            for (uint32_t q = 0; q < e.n; q++) {
+                const double x = __ull2double_rn(v[q]);
+                prev = __dadd_rn(__dmul_rn(0.5, prev), __dmul_rn(0.5, x));
+                count += (fabs(__dsub_rn(x, prev)) > sd) ? 1u : 0u;
+            }
+        }
+    }
+    const uint32_t pre = block_exclusive_scan<NT>(count, warp_sums, &total_s);
+    if (threadIdx.x == 0) base_s = total_s ? atomicAdd(&stats[ST_OUTCOUNT], total_s) : 0u;
+    __syncthreads();
+    if (count == 0) return;
+    uint32_t idx = base_s + pre;
+    const uint32_t *t = csr_t + e.off;
+    double prev = 0.0;
+    for (uint32_t q = 0; q < e.n; q++) {
+        const double x = __ull2double_rn(v[q]);
+        prev = __dadd_rn(__dmul_rn(0.5, prev), __dmul_rn(0.5, x));
+        const bool flag = has_sd && (fabs(__dsub_rn(x, prev)) > sd);
+        if (flag || emit_all) {
+            if (idx < out_cap) write_out(out, idx, e, t[q], sd, prev, x, flag);
+            idx++;
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------
+// launchers
+// ----------------------------------------------------------------------------------------
+static int g_num_sms = 0;
+static int num_sms()
+{
+    if (!g_num_sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (g_num_sms <= 0) g_num_sms = 148;
+    }
+    return g_num_sms;
+}
+
+static bool cols_aligned16(const ColPtrs &c)
+{
+    auto ok = [](const void *p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+    return ok(c.src_ip) && ok(c.dst_ip) && ok(c.flow_start) && ok(c.flow_end) && ok(c.src_port) && ok(c.dst_port) &&
+           ok(c.proto) && ok(c.value);
+}
+
+static uint32_t partition_grid(uint64_t R)
+{
+    const uint64_t groups = (R + 7) / 8;
+    const uint64_t want = (groups + 255) / 256;
+    const uint64_t cap = (uint64_t)num_sms() * 8;           // 8 resident CTAs of 256 threads per SM
+    return (uint32_t)(want < cap ? (want ? want : 1) : cap);
+}
+
+cudaError_t launch_hist(cudaStream_t st, const ColPtrs &c, uint64_t R, const RowFilter &f, int logB, uint32_t *hist)
+{
+    if (R == 0) return cudaSuccess;
+    const int bshift = 64 - logB;
+    if (cols_aligned16(c))
+        partition_kernel<false, true><<<partition_grid(R), 256, 0, st>>>(c, R, f, bshift, hist, nullptr);
+    else
+        partition_kernel<false, false><<<partition_grid(R), 256, 0, st>>>(c, R, f, bshift, hist, nullptr);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_scatter(cudaStream_t st, const ColPtrs &c, uint64_t R, const RowFilter &f, int logB, uint32_t *cursor,
+                           Row32 *part)
+{
+    if (R == 0) return cudaSuccess;
+    const int bshift = 64 - logB;
+    if (cols_aligned16(c))
+        partition_kernel<true, true><<<partition_grid(R), 256, 0, st>>>(c, R, f, bshift, cursor, part);
+    else
+        partition_kernel<true, false><<<partition_grid(R), 256, 0, st>>>(c, R, f, bshift, cursor, part);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_bucket_scan(cudaStream_t st, const uint32_t *hist, uint32_t *offsets, uint32_t *cursor, uint32_t B,
+                               uint32_t cap, uint32_t *big_list, uint32_t big_cap, uint32_t *stats)
+{
+    bucket_scan_kernel<<<1, 1024, 0, st>>>(hist, offsets, cursor, B, cap, big_list, big_cap, stats);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_group(cudaStream_t st, Row32 *part, const uint32_t *offsets, uint32_t B, int logB, uint64_t *csr_v,
+                         uint32_t *csr_t, uint32_t *nsb, uint32_t *npb, int reducer)
+{
+    using S = GroupSmem<kGroupCap, kGroupThreads>;
+    static bool configured = false;
+    auto kern = group_kernel<kGroupCap, kGroupThreads>;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(S));
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    int sshift = 64 - logB - 12;          // 12 hash bits below the bucket bits pick the slot
+    if (sshift < 0) sshift = 0;
+    kern<<<B, kGroupThreads, sizeof(S), st>>>(part, offsets, sshift, csr_v, csr_t, nsb, npb, reducer);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_series_scan(cudaStream_t st, const uint32_t *nsb, const uint32_t *npb, uint32_t *sbase, uint32_t B,
+                               uint32_t *stats)
+{
+    series_scan_kernel<<<1, 1024, 0, st>>>(nsb, npb, sbase, B, stats);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_detect_ewma(cudaStream_t st, const Row32 *part, const uint32_t *offsets, const uint32_t *sbase, uint32_t B,
+                               uint32_t S, const uint64_t *csr_v, const uint32_t *csr_t, const OutCols &out,
+                               uint32_t out_cap, uint32_t *stats, int emit_all)
+{
+    if (S == 0) return cudaSuccess;
+    constexpr int NT = 128;
+    detect_ewma_kernel<NT><<<(S + NT - 1) / NT, NT, 0, st>>>(part, offsets, sbase, B, S, csr_v, csr_t, out, out_cap, stats,
+                                                            emit_all);
+    return cudaGetLastError();
+}
+
+}  // namespace tad
