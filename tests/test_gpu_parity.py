@@ -104,3 +104,88 @@ def test_job_state_machine(engine):
     assert st["state"] == "COMPLETED" and st["completed_stages"] == st["total_stages"]
     job.release()
     cols.free()
+
+
+# ------------------------------------------------------------------------------------------------
+# DBSCAN (anomaly_detection.py:325-349)
+# ------------------------------------------------------------------------------------------------
+def test_e2e_fixture_dbscan(engine):
+    t = synth.golden_e2e_table(REF["throughput_list"], duplicates=1)
+    got, st = run_both(engine, t, "DBSCAN")
+    assert list((np.sort(got["flow_end"]) - (synth.T0 + 3600)) // 60) == [58, 60, 68, 80, 88]
+    assert (got["algo_calc"] == 0.0).all()
+    allp, _ = run_both(engine, synth.golden_e2e_table(REF["throughput_list"]), "DBSCAN", emit_all=True)
+    order = np.argsort(allp["flow_end"])
+    assert list(allp["anomaly"][order].astype(bool)) == REF["expected_dbscan_anomaly_list"]
+
+
+@pytest.mark.parametrize("kw", [
+    dict(n_series=100, points_per_series=100, seed=21),
+    dict(n_series=4000, points_per_series=24, seed=22),                      # configs[3] shape: series length 24
+    dict(n_series=3000, points_per_series=8, seed=23, ragged=True),          # n <= 11: sklearn brute-force regime
+    dict(n_series=500, points_per_series=40, seed=24, dup_frac=0.3, ragged=True),
+    dict(n_series=20000, points_per_series=100, seed=25),
+])
+@pytest.mark.parametrize("emit_all", [False, True])
+def test_synthetic_dbscan(engine, kw, emit_all):
+    run_both(engine, synth.make_flows(**kw), "DBSCAN", emit_all=emit_all)
+
+
+def test_dbscan_golden_udf_cases(engine):
+    """Every seeded series of tests/golden/udf_cases.json (outputs of the reference UDF itself, incl. exact-eps
+    ties and > 2^53 values) as one table: one connection per case."""
+    cases = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "udf_cases.json")))["cases"]
+    cols = {k: [] for k in synth.COLUMN_DTYPES}
+    for ci, c in enumerate(cases):
+        n = len(c["values"])
+        cols["src_ip"].append(np.full(n, 0x0A000000 + ci, np.uint32)); cols["dst_ip"].append(np.full(n, 0x0A010000, np.uint32))
+        cols["src_port"].append(np.full(n, 1000 + ci, np.uint16)); cols["dst_port"].append(np.full(n, 443, np.uint16))
+        cols["proto"].append(np.full(n, 6, np.uint8)); cols["flow_start"].append(np.full(n, synth.T0, np.uint32))
+        cols["flow_end"].append((synth.T0 + 60 * (1 + np.arange(n))).astype(np.uint32))
+        cols["value"].append(np.array(c["values"], dtype=np.uint64))
+    t = {k: np.concatenate(v) for k, v in cols.items()}
+    perm = np.random.default_rng(5).permutation(len(t["value"]))
+    t = {k: v[perm] for k, v in t.items()}
+    for algo, key in (("DBSCAN", "dbscan_flags"), ("EWMA", "ewma")):
+        got, st = run_both(engine, t, algo, emit_all=True)
+        for ci, c in enumerate(cases):
+            m = got["src_ip"] == 0x0A000000 + ci
+            order = np.argsort(got["flow_end"][m])
+            if algo == "DBSCAN":
+                assert list(got["anomaly"][m][order].astype(bool)) == c["dbscan_flags"], c["tag"]
+            else:
+                assert list(got["algo_calc"][m][order]) == c["ewma"], c["tag"]
+
+
+# ------------------------------------------------------------------------------------------------
+# oversized buckets -> spill path
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("algo", ["EWMA", "DBSCAN"])
+def test_long_series_spill(engine, algo):
+    """Connections longer than the shared-memory bucket capacity (2048 rows) take the global path."""
+    t1 = synth.make_flows(3, 5000, seed=31, dup_frac=0.05)
+    t2 = synth.make_flows(3000, 20, seed=32)
+    t = {k: np.concatenate([t1[k], t2[k]]) for k in t1}
+    got, st = run_both(engine, t, algo, emit_all=True)
+    assert st["spill_rows"] >= 15000
+
+
+@pytest.fixture(scope="module")
+def tiny_bucket_engine():
+    """Engine forced to 2 hash buckets: every table of more than a few thousand rows spills."""
+    from theia_b200.engine import TadEngine
+    os.environ["TAD_DEBUG_LOGB"] = "1"
+    try:
+        eng = TadEngine(device=0)
+    finally:
+        del os.environ["TAD_DEBUG_LOGB"]
+    yield eng
+    eng.close()
+
+
+@pytest.mark.parametrize("algo", ["EWMA", "DBSCAN"])
+def test_forced_spill_everything(tiny_bucket_engine, algo):
+    t = synth.make_flows(800, 30, seed=33, dup_frac=0.1, ragged=True)
+    got, st = run_both(tiny_bucket_engine, t, algo, emit_all=True)
+    assert st["spill_rows"] == st["rows_kept"]
+    got, st = run_both(tiny_bucket_engine, t, algo, reducer=1)

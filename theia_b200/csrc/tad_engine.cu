@@ -68,7 +68,7 @@ struct tad_ctx {
     int debug_logb = -1;
     int num_sms = 148;
     // device workspace (grow-only, reused across jobs; jobs are serialized by the worker)
-    DevBuf d_col[10], hist, offsets, cursor, big_list, stats, part, csr_v, csr_t, nsb, npb, sbase, outb, ns_ignore, spill,
+    DevBuf d_col[10], hist, offsets, cursor, big_list, big_base, csr_p, stats, part, csr_v, csr_t, nsb, npb, sbase, outb, ns_ignore, spill,
         dbx, dbi, exch;
     uint32_t *h_stats = nullptr;   // pinned readback of the device scalars
     std::mutex pool_mu;
@@ -292,6 +292,7 @@ void run_job(tad_ctx *ctx, tad_job *job)
     ensure(ctx->offsets, ((size_t)B + 1) * 4);
     ensure(ctx->cursor, (size_t)B * 4);
     ensure(ctx->big_list, (size_t)B * 4);
+    ensure(ctx->big_base, ((size_t)B + 1) * 4);
     ensure(ctx->nsb, (size_t)B * 4);
     ensure(ctx->npb, (size_t)B * 4);
     ensure(ctx->sbase, ((size_t)B + 1) * 4);
@@ -299,6 +300,7 @@ void run_job(tad_ctx *ctx, tad_job *job)
     ensure(ctx->csr_v, (R ? R : 1) * 8);
     ensure(ctx->csr_t, (R ? R : 1) * 4);
     uint32_t *hist = (uint32_t *)ctx->hist.p, *offsets = (uint32_t *)ctx->offsets.p, *cursor = (uint32_t *)ctx->cursor.p;
+    uint32_t *big_base = (uint32_t *)ctx->big_base.p;
     uint32_t *big_list = (uint32_t *)ctx->big_list.p, *nsb = (uint32_t *)ctx->nsb.p, *npb = (uint32_t *)ctx->npb.p;
     uint32_t *sbase = (uint32_t *)ctx->sbase.p;
     Row32 *part = (Row32 *)ctx->part.p;
@@ -311,7 +313,7 @@ void run_job(tad_ctx *ctx, tad_job *job)
     mark(-1);
     CU(launch_hist(st, c, R, f, logB, hist)); launches += R ? 1 : 0;
     mark(TAD_PHASE_HIST);
-    CU(launch_bucket_scan(st, hist, offsets, cursor, B, kGroupCap, big_list, B, d_stats)); launches++;
+    CU(launch_bucket_scan(st, hist, offsets, cursor, B, kGroupCap, big_list, big_base, d_stats)); launches++;
     mark(TAD_PHASE_SCAN);
     CU(launch_scatter(st, c, R, f, logB, cursor, part)); launches += R ? 1 : 0;
     mark(TAD_PHASE_SCATTER);
@@ -324,15 +326,20 @@ void run_job(tad_ctx *ctx, tad_job *job)
     set_progress(job, TAD_STATE_RUNNING, 3);    // ingest, partition, exchange (single GPU: no-op)
 
     // ---- group ------------------------------------------------------------------------------
+    uint32_t *csr_p = nullptr;
+    if (sp.algo == TAD_ALGO_DBSCAN) {
+        ensure(ctx->csr_p, (R ? R : 1) * 4);
+        csr_p = (uint32_t *)ctx->csr_p.p;
+    }
     mark(-1);
-    CU(launch_group(st, part, offsets, B, logB, csr_v, csr_t, nsb, npb, sp.reducer)); launches++;
+    CU(launch_group(st, part, offsets, B, logB, csr_v, csr_t, csr_p, nsb, npb, sp.reducer)); launches++;
     mark(TAD_PHASE_GROUP);
     if (n_big) {
         const size_t need = spill_scratch_bytes(big_rows);
         ensure(ctx->spill, need);
         int l = 0;
-        CU(run_spill(st, part, offsets, big_list, n_big, big_rows, ctx->spill.p, ctx->spill.cap, csr_v, csr_t, nsb, npb,
-                     sp.reducer, &l));
+        CU(run_spill(st, part, offsets, big_list, big_base, n_big, big_rows, ctx->spill.p, ctx->spill.cap, csr_v, csr_t, nsb,
+                     npb, sp.reducer, &l));
         launches += l;
         mark(TAD_PHASE_SPILL);
     }
@@ -362,10 +369,10 @@ void run_job(tad_ctx *ctx, tad_job *job)
             CU(launch_detect_ewma(st, part, offsets, sbase, B, S, csr_v, csr_t, oc, (uint32_t)out_cap, d_stats, emit_all));
             launches += S ? 1 : 0;
         } else if (sp.algo == TAD_ALGO_DBSCAN) {
-            ensure(ctx->dbx, (points ? points : 1) * 8);
-            ensure(ctx->dbi, (points ? points : 1) * 4);
-            CU(launch_detect_dbscan(st, part, offsets, sbase, B, S, csr_v, csr_t, (double *)ctx->dbx.p, (uint32_t *)ctx->dbi.p,
-                                    oc, (uint32_t)out_cap, d_stats, emit_all));
+            ensure(ctx->dbx, (R ? R : 1) * 4);      // prefix count of core points, per point slot
+            ensure(ctx->dbi, (R ? R : 1));          // noise flag, per point slot
+            CU(launch_detect_dbscan(st, part, offsets, sbase, B, S, csr_v, csr_t, csr_p, (uint32_t *)ctx->dbx.p,
+                                    (uint8_t *)ctx->dbi.p, oc, (uint32_t)out_cap, d_stats, emit_all));
             launches += S ? 1 : 0;
         } else {
             fail(TAD_ERR_UNSUPPORTED, "algorithm %d is not implemented by this build", sp.algo);
@@ -569,7 +576,7 @@ void tad_shutdown(tad_ctx *ctx)
     if (ctx->worker.joinable()) ctx->worker.join();
     cudaSetDevice(ctx->cfg.device);
     nccl_comm_destroy(&ctx->nccl);
-    DevBuf *bufs[] = {&ctx->hist, &ctx->offsets, &ctx->cursor, &ctx->big_list, &ctx->stats, &ctx->part, &ctx->csr_v,
+    DevBuf *bufs[] = {&ctx->hist, &ctx->offsets, &ctx->cursor, &ctx->big_list, &ctx->big_base, &ctx->csr_p, &ctx->stats, &ctx->part, &ctx->csr_v,
                       &ctx->csr_t, &ctx->nsb, &ctx->npb, &ctx->sbase, &ctx->outb, &ctx->ns_ignore, &ctx->spill, &ctx->dbx,
                       &ctx->dbi, &ctx->exch};
     for (DevBuf *b : bufs)

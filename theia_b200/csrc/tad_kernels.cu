@@ -194,41 +194,51 @@ __device__ __forceinline__ uint32_t block_exclusive_scan_1024(uint32_t v, uint32
     return warp_sums[warp] + inc - v;
 }
 
-// offsets[B+1] = exclusive scan of hist; cursor = copy of offsets; lists buckets > cap.
+// offsets[B+1] = exclusive scan of hist; cursor = copy of offsets; lists the buckets larger
+// than `cap` in ascending bucket order together with the exclusive scan of their sizes
+// (big_base[n_big+1]) -- the spill path relies on that order.
 __global__ void __launch_bounds__(1024) bucket_scan_kernel(const uint32_t *__restrict__ hist, uint32_t *__restrict__ offsets,
                                                            uint32_t *__restrict__ cursor, uint32_t B, uint32_t cap,
-                                                           uint32_t *__restrict__ big_list, uint32_t big_cap,
+                                                           uint32_t *__restrict__ big_list, uint32_t *__restrict__ big_base,
                                                            uint32_t *__restrict__ stats)
 {
-    __shared__ uint32_t total_s;
-    __shared__ uint32_t nbig_s, maxb_s;
-    __shared__ unsigned long long bigrows_s;
-    if (threadIdx.x == 0) { nbig_s = 0; maxb_s = 0; bigrows_s = 0; }
+    __shared__ uint32_t total_s, nbig_s, bigrows_s, maxb_s;
+    if (threadIdx.x == 0) maxb_s = 0;
     const uint32_t per = (B + 1023) / 1024;
     const uint32_t lo = min(B, threadIdx.x * per), hi = min(B, lo + per);
-    uint32_t sum = 0;
-    for (uint32_t i = lo; i < hi; i++) sum += hist[i];
+    uint32_t sum = 0, nbig = 0, bigrows = 0, mx = 0;
+    for (uint32_t i = lo; i < hi; i++) {
+        const uint32_t h = hist[i];
+        sum += h;
+        mx = max(mx, h);
+        if (h > cap) { nbig++; bigrows += h; }
+    }
     const uint32_t pre = block_exclusive_scan_1024(sum, &total_s);
-    uint32_t run = pre, mx = 0;
+    __syncthreads();
+    const uint32_t pre_nbig = block_exclusive_scan_1024(nbig, &nbig_s);
+    __syncthreads();
+    const uint32_t pre_rows = block_exclusive_scan_1024(bigrows, &bigrows_s);
+    uint32_t run = pre, k = pre_nbig, br = pre_rows;
     for (uint32_t i = lo; i < hi; i++) {
         const uint32_t h = hist[i];
         offsets[i] = run;
         cursor[i] = run;
         run += h;
-        mx = max(mx, h);
         if (h > cap) {
-            const uint32_t k = atomicAdd(&nbig_s, 1u);
-            if (k < big_cap) big_list[k] = i;
-            atomicAdd(&bigrows_s, (unsigned long long)h);
+            big_list[k] = i;
+            big_base[k] = br;
+            k++;
+            br += h;
         }
     }
     atomicMax(&maxb_s, mx);
     __syncthreads();
     if (threadIdx.x == 0) {
         offsets[B] = total_s;
+        big_base[nbig_s] = bigrows_s;
         stats[ST_KEPT] = total_s;
         stats[ST_NBIG] = nbig_s;
-        stats[ST_BIGROWS] = (uint32_t)bigrows_s;
+        stats[ST_BIGROWS] = bigrows_s;
         stats[ST_MAXBUCKET] = maxb_s;
     }
 }
@@ -299,10 +309,11 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *w
     return warp_sums[warp] + inc - v;
 }
 
-template <int CAP, int NT>
+template <int CAP, int NT, bool VRANK>
 __global__ void __launch_bounds__(NT) group_kernel(Row32 *__restrict__ part, const uint32_t *__restrict__ offsets, int sshift,
                                                    uint64_t *__restrict__ csr_v, uint32_t *__restrict__ csr_t,
-                                                   uint32_t *__restrict__ nsb, uint32_t *__restrict__ npb, int reducer)
+                                                   uint32_t *__restrict__ csr_p, uint32_t *__restrict__ nsb,
+                                                   uint32_t *__restrict__ npb, int reducer)
 {
     using S = GroupSmem<CAP, NT>;
     constexpr int HT = S::HT;
@@ -414,6 +425,8 @@ __global__ void __launch_bounds__(NT) group_kernel(Row32 *__restrict__ part, con
     uint32_t *ts = reinterpret_cast<uint32_t *>(s.x);
     uint32_t *tout = ts + CAP;
     unsigned long long *vout = reinterpret_cast<unsigned long long *>(s.x + 8 * CAP);
+    uint16_t *pslot = reinterpret_cast<uint16_t *>(s.x + 16 * CAP);   // VRANK: slot of the series at each position
+    uint16_t *pout = reinterpret_cast<uint16_t *>(s.x + 18 * CAP);    // VRANK: value rank -> time index
 
 #pragma unroll
     for (int j = 0; j < RPT; j++) {
@@ -443,6 +456,7 @@ __global__ void __launch_bounds__(NT) group_kernel(Row32 *__restrict__ part, con
             }
             tout[so + rank] = t;
             vout[so + rank] = myV[j];
+            if (VRANK) pslot[so + rank] = (uint16_t)slot;
             mySP[j] = (so + rank) | ((rank ? 1u : 0u) << 31);
         }
     }
@@ -480,6 +494,7 @@ __global__ void __launch_bounds__(NT) group_kernel(Row32 *__restrict__ part, con
             if (wr + 1 != cnt) {
                 removed += cnt - (wr + 1);
                 ent[w & 0xffffu].n = wr + 1;
+                s.ht[sl] = ((wr + 1) << 16) | (w & 0xffffu);
             }
         }
         __syncthreads();
@@ -488,10 +503,31 @@ __global__ void __launch_bounds__(NT) group_kernel(Row32 *__restrict__ part, con
         points = n - s.total;
     }
 
+    if (VRANK) {
+        // ---- V: rank every point inside its series by (value, time index) for the DBSCAN sweep ----
+        __syncthreads();
+        for (uint32_t p = tid; p < n; p += NT) {
+            const uint32_t slot = pslot[p];
+            const uint32_t so = s.soff[slot], cnt = s.ht[slot] >> 16, me = p - so;
+            if (me >= cnt) continue;                    // hole left by the duplicate reduce
+            const unsigned long long v = vout[p];
+            const unsigned long long *vs = vout + so;
+            uint32_t rank = 0;
+#pragma unroll 4
+            for (uint32_t q = 0; q < cnt; q++) {
+                const unsigned long long vq = vs[q];
+                rank += (vq < v || (vq == v && q < me)) ? 1u : 0u;
+            }
+            pout[so + rank] = (uint16_t)me;
+        }
+        __syncthreads();
+    }
+
     // ---- W: coalesced write of the per-series arrays ------------------------------------
     for (uint32_t p = tid; p < n; p += NT) {
         csr_t[off_b + p] = tout[p];
         csr_v[off_b + p] = vout[p];
+        if (VRANK) csr_p[off_b + p] = pout[p];
     }
     if (tid == 0) { nsb[bkt] = ns; npb[bkt] = points; }
 }
@@ -596,6 +632,117 @@ __global__ void __launch_bounds__(NT) detect_ewma_kernel(const Row32 *__restrict
 }
 
 // ----------------------------------------------------------------------------------------
+// K4 (DBSCAN): exact 1-D rule of sklearn's DBSCAN(min_samples=4, eps=2.5e8)
+// (anomaly_detection.py:325-349; oracle/tad_oracle.py:calculate_dbscan_anomaly)
+// ----------------------------------------------------------------------------------------
+#define TAD_DBSCAN_EPS 250000000.0
+#define TAD_DBSCAN_MIN 4u
+
+// squared distance exactly as sklearn's brute-force radius search evaluates it (n <= 11)
+__device__ __forceinline__ double sk_brute_d2(double xi, double xj)
+{
+    const double d = __dadd_rn(__dadd_rn(__dmul_rn(xi, xi), __dmul_rn(-2.0, __dmul_rn(xi, xj))), __dmul_rn(xj, xj));
+    return d > 0.0 ? d : 0.0;
+}
+__device__ __forceinline__ bool within_eps(double a, double b) { return fabs(__dsub_rn(a, b)) <= TAD_DBSCAN_EPS; }
+
+template <int NT>
+__global__ void __launch_bounds__(NT) detect_dbscan_kernel(const Row32 *__restrict__ part, const uint32_t *__restrict__ offsets,
+                                                           const uint32_t *__restrict__ sbase, uint32_t B, uint32_t S,
+                                                           const uint64_t *__restrict__ csr_v, const uint32_t *__restrict__ csr_t,
+                                                           uint32_t *__restrict__ csr_p, uint32_t *__restrict__ scratch_pc,
+                                                           uint8_t *__restrict__ scratch_flag, OutCols out, uint32_t out_cap,
+                                                           uint32_t *__restrict__ stats, int emit_all)
+{
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t total_s, base_s;
+    const uint32_t i = blockIdx.x * NT + threadIdx.x;
+    SeriesEntry e;
+    e.n = 0;
+    const uint64_t *v = nullptr;
+    uint8_t *flag = nullptr;
+    bool has_sd = false;
+    double sd = 0.0;
+    uint32_t count = 0;
+    if (i < S) {
+        const uint32_t b = find_bucket(sbase, B, i);
+        const uint4 *p = reinterpret_cast<const uint4 *>(part + offsets[b] + (i - sbase[b]));
+        const uint4 k = p[0], w = p[1];
+        e.a = pack64(k.x, k.y); e.b = pack64(k.z, k.w); e.proto = w.x; e.n = w.y; e.off = w.z; e.pad = w.w;
+        v = csr_v + e.off;
+        flag = scratch_flag + e.off;
+        const uint32_t n = e.n;
+        sd = series_stddev(v, n, has_sd);
+        if (n <= 11) {
+            const double r2 = TAD_DBSCAN_EPS * TAD_DBSCAN_EPS;
+            uint32_t core = 0;
+            for (uint32_t a = 0; a < n; a++) {
+                const double xa = __ull2double_rn(v[a]);
+                uint32_t c = 0;
+                for (uint32_t q = 0; q < n; q++) c += (a == q || sk_brute_d2(xa, __ull2double_rn(v[q])) <= r2) ? 1u : 0u;
+                core |= (c >= TAD_DBSCAN_MIN ? 1u : 0u) << a;
+            }
+            for (uint32_t a = 0; a < n; a++) {
+                const double xa = __ull2double_rn(v[a]);
+                bool reach = (core >> a) & 1u;
+                for (uint32_t q = 0; q < n && !reach; q++)
+                    reach = ((core >> q) & 1u) && (a == q || sk_brute_d2(xa, __ull2double_rn(v[q])) <= r2);
+                flag[a] = reach ? 0 : 1;
+                count += reach ? 0u : 1u;
+            }
+        } else {
+            uint32_t *perm = csr_p + e.off;
+            uint32_t *pc = scratch_pc + e.off;           // pc[k] = cores among sorted positions 0..k
+            if (e.pad) {                                 // series from the spill path: rank by value here
+                for (uint32_t a = 0; a < n; a++) {
+                    const uint64_t va = v[a];
+                    uint32_t rank = 0;
+                    for (uint32_t q = 0; q < n; q++) {
+                        const uint64_t vq = v[q];
+                        rank += (vq < va || (vq == va && q < a)) ? 1u : 0u;
+                    }
+                    perm[rank] = a;
+                }
+            }
+            uint32_t lo = 0, hi = 0, run = 0;
+            for (uint32_t k = 0; k < n; k++) {
+                const double xk = __ull2double_rn(v[perm[k]]);
+                while (!within_eps(xk, __ull2double_rn(v[perm[lo]]))) lo++;
+                if (hi < k) hi = k;
+                while (hi + 1 < n && within_eps(__ull2double_rn(v[perm[hi + 1]]), xk)) hi++;
+                run += (hi - lo + 1 >= TAD_DBSCAN_MIN) ? 1u : 0u;
+                pc[k] = run;
+            }
+            lo = 0; hi = 0;
+            for (uint32_t k = 0; k < n; k++) {
+                const uint32_t pk = perm[k];
+                const double xk = __ull2double_rn(v[pk]);
+                while (!within_eps(xk, __ull2double_rn(v[perm[lo]]))) lo++;
+                if (hi < k) hi = k;
+                while (hi + 1 < n && within_eps(__ull2double_rn(v[perm[hi + 1]]), xk)) hi++;
+                const uint32_t cores = pc[hi] - (lo ? pc[lo - 1] : 0u);
+                flag[pk] = cores == 0 ? 1 : 0;
+                count += cores == 0 ? 1u : 0u;
+            }
+        }
+        if (emit_all) count = n;
+    }
+    const uint32_t pre = block_exclusive_scan<NT>(count, warp_sums, &total_s);
+    if (threadIdx.x == 0) base_s = total_s ? atomicAdd(&stats[ST_OUTCOUNT], total_s) : 0u;
+    __syncthreads();
+    if (count == 0) return;
+    uint32_t idx = base_s + pre;
+    const uint32_t *t = csr_t + e.off;
+    for (uint32_t q = 0; q < e.n; q++) {
+        const bool f = flag[q] != 0;
+        if (f || emit_all) {
+            if (idx < out_cap) write_out(out, idx, e, t[q], sd, 0.0, __ull2double_rn(v[q]), f);
+            idx++;
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------
 // launchers
 // ----------------------------------------------------------------------------------------
 static int g_num_sms = 0;
@@ -649,26 +796,31 @@ cudaError_t launch_scatter(cudaStream_t st, const ColPtrs &c, uint64_t R, const 
 }
 
 cudaError_t launch_bucket_scan(cudaStream_t st, const uint32_t *hist, uint32_t *offsets, uint32_t *cursor, uint32_t B,
-                               uint32_t cap, uint32_t *big_list, uint32_t big_cap, uint32_t *stats)
+                               uint32_t cap, uint32_t *big_list, uint32_t *big_base, uint32_t *stats)
 {
-    bucket_scan_kernel<<<1, 1024, 0, st>>>(hist, offsets, cursor, B, cap, big_list, big_cap, stats);
+    bucket_scan_kernel<<<1, 1024, 0, st>>>(hist, offsets, cursor, B, cap, big_list, big_base, stats);
     return cudaGetLastError();
 }
 
 cudaError_t launch_group(cudaStream_t st, Row32 *part, const uint32_t *offsets, uint32_t B, int logB, uint64_t *csr_v,
-                         uint32_t *csr_t, uint32_t *nsb, uint32_t *npb, int reducer)
+                         uint32_t *csr_t, uint32_t *csr_p, uint32_t *nsb, uint32_t *npb, int reducer)
 {
     using S = GroupSmem<kGroupCap, kGroupThreads>;
     static bool configured = false;
-    auto kern = group_kernel<kGroupCap, kGroupThreads>;
+    auto kern = group_kernel<kGroupCap, kGroupThreads, false>;
+    auto kern_v = group_kernel<kGroupCap, kGroupThreads, true>;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(S));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(kern_v, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(S));
         if (e != cudaSuccess) return e;
         configured = true;
     }
     int sshift = 64 - logB - 12;          // 12 hash bits below the bucket bits pick the slot
     if (sshift < 0) sshift = 0;
-    kern<<<B, kGroupThreads, sizeof(S), st>>>(part, offsets, sshift, csr_v, csr_t, nsb, npb, reducer);
+    if (csr_p)
+        kern_v<<<B, kGroupThreads, sizeof(S), st>>>(part, offsets, sshift, csr_v, csr_t, csr_p, nsb, npb, reducer);
+    else
+        kern<<<B, kGroupThreads, sizeof(S), st>>>(part, offsets, sshift, csr_v, csr_t, csr_p, nsb, npb, reducer);
     return cudaGetLastError();
 }
 
@@ -687,6 +839,19 @@ cudaError_t launch_detect_ewma(cudaStream_t st, const Row32 *part, const uint32_
     constexpr int NT = 128;
     detect_ewma_kernel<NT><<<(S + NT - 1) / NT, NT, 0, st>>>(part, offsets, sbase, B, S, csr_v, csr_t, out, out_cap, stats,
                                                             emit_all);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_detect_dbscan(cudaStream_t st, const Row32 *part, const uint32_t *offsets, const uint32_t *sbase,
+                                 uint32_t B, uint32_t S, const uint64_t *csr_v, const uint32_t *csr_t, const uint32_t *csr_p,
+                                 uint32_t *scratch_pc, uint8_t *scratch_flag, const OutCols &out, uint32_t out_cap,
+                                 uint32_t *stats, int emit_all)
+{
+    if (S == 0) return cudaSuccess;
+    constexpr int NT = 128;
+    detect_dbscan_kernel<NT><<<(S + NT - 1) / NT, NT, 0, st>>>(part, offsets, sbase, B, S, csr_v, csr_t,
+                                                              const_cast<uint32_t *>(csr_p), scratch_pc, scratch_flag, out,
+                                                              out_cap, stats, emit_all);
     return cudaGetLastError();
 }
 
