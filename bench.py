@@ -179,6 +179,12 @@ def run_ours(args):
     total_rows = rows * world
 
     # ---- e2e: host (pinned) buffers through the C ABI, H2D + D2H inside the timed region --------
+    if args.no_e2e:
+        if rank == 0:
+            print(json.dumps({"value": total_rows / (ms_dev * 1e-3), "ms_per_step": ms_dev,
+                              "phase_ms": {k: v / args.steps for k, v in phase.items()}, "note": "profiling run"}))
+        eng.close()
+        return
     hcols = eng.alloc_columns(rows)
     for name, tns in cols_t.items():
         hv = hcols.view(name)
@@ -257,6 +263,7 @@ def main():
     ap.add_argument("--points", type=int, default=100)
     ap.add_argument("--ref-series", type=int, default=100_000, help="connections in the CPU sample")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs: skip the host-buffer leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -79,6 +79,7 @@ enum {
 };
 
 constexpr int kGroupCap = 2048;       // rows a bucket may hold to take the shared-memory path
+constexpr int kGroupCapSmall = 1024;  // first capacity class (higher occupancy)
 constexpr int kGroupThreads = 256;
 constexpr int kGroupHT = 2 * kGroupCap;
 

@@ -69,7 +69,8 @@ struct tad_ctx {
     int num_sms = 148;
     // device workspace (grow-only, reused across jobs; jobs are serialized by the worker)
     DevBuf d_col[10], hist, offsets, cursor, big_list, big_base, csr_p, stats, part, csr_v, csr_t, nsb, npb, sbase, outb, ns_ignore, spill,
-        dbx, dbi, exch;
+        dbx, dbi, exch, scan_sync;
+    uint32_t scan_epoch = 0;
     uint32_t *h_stats = nullptr;   // pinned readback of the device scalars
     std::mutex pool_mu;
     std::vector<PinnedBlock> pinned_pool;
@@ -251,6 +252,10 @@ void run_job(tad_ctx *ctx, tad_job *job)
     ensure(ctx->stats, 64 * sizeof(uint32_t));
     uint32_t *d_stats = static_cast<uint32_t *>(ctx->stats.p);
     CU(cudaMemsetAsync(d_stats, 0, 64 * sizeof(uint32_t), st));
+    if (!ctx->scan_sync.p) {
+        ensure(ctx->scan_sync, scan_sync_bytes());
+        CU(cudaMemsetAsync(ctx->scan_sync.p, 0, scan_sync_bytes(), st));
+    }
 
     // ---- ingest: host columns -> device (device-resident columns are used in place) -------
     ColPtrs c{};
@@ -313,7 +318,8 @@ void run_job(tad_ctx *ctx, tad_job *job)
     mark(-1);
     CU(launch_hist(st, c, R, f, logB, hist)); launches += R ? 1 : 0;
     mark(TAD_PHASE_HIST);
-    CU(launch_bucket_scan(st, hist, offsets, cursor, B, kGroupCap, big_list, big_base, d_stats)); launches++;
+    CU(launch_bucket_scan(st, hist, offsets, cursor, B, kGroupCap, big_list, big_base, d_stats, ctx->scan_sync.p,
+                          ++ctx->scan_epoch)); launches++;
     mark(TAD_PHASE_SCAN);
     CU(launch_scatter(st, c, R, f, logB, cursor, part)); launches += R ? 1 : 0;
     mark(TAD_PHASE_SCATTER);
@@ -332,7 +338,7 @@ void run_job(tad_ctx *ctx, tad_job *job)
         csr_p = (uint32_t *)ctx->csr_p.p;
     }
     mark(-1);
-    CU(launch_group(st, part, offsets, B, logB, csr_v, csr_t, csr_p, nsb, npb, sp.reducer)); launches++;
+    CU(launch_group(st, part, offsets, B, logB, csr_v, csr_t, csr_p, nsb, npb, sp.reducer)); launches += 2;
     mark(TAD_PHASE_GROUP);
     if (n_big) {
         const size_t need = spill_scratch_bytes(big_rows);
@@ -343,7 +349,7 @@ void run_job(tad_ctx *ctx, tad_job *job)
         launches += l;
         mark(TAD_PHASE_SPILL);
     }
-    CU(launch_series_scan(st, nsb, npb, sbase, B, d_stats)); launches++;
+    CU(launch_series_scan(st, nsb, npb, sbase, B, d_stats, ctx->scan_sync.p, ++ctx->scan_epoch)); launches++;
     CU(cudaMemcpyAsync(ctx->h_stats, d_stats, ST_COUNT * 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     check_cancel();
@@ -578,7 +584,7 @@ void tad_shutdown(tad_ctx *ctx)
     nccl_comm_destroy(&ctx->nccl);
     DevBuf *bufs[] = {&ctx->hist, &ctx->offsets, &ctx->cursor, &ctx->big_list, &ctx->big_base, &ctx->csr_p, &ctx->stats, &ctx->part, &ctx->csr_v,
                       &ctx->csr_t, &ctx->nsb, &ctx->npb, &ctx->sbase, &ctx->outb, &ctx->ns_ignore, &ctx->spill, &ctx->dbx,
-                      &ctx->dbi, &ctx->exch};
+                      &ctx->dbi, &ctx->exch, &ctx->scan_sync};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     for (int i = 0; i < 10; i++)

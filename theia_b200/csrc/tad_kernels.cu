@@ -35,10 +35,12 @@ __device__ __forceinline__ uint2 ldg_stream64(const void *p)
     asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
     return r;
 }
-__device__ __forceinline__ void stg128(void *p, uint4 v)
+// one 32-byte row = one 256-bit store = one full DRAM sector per request (sm_100: STG.E.256)
+__device__ __forceinline__ void stg256(void *p, uint4 lo, uint4 hi)
 {
-    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};"
-                 :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    asm volatile("st.global.L1::no_allocate.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "l"(p), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w)
+                 : "memory");
 }
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
 {
@@ -82,9 +84,8 @@ __device__ __forceinline__ void emit_row(const RowRegs &r, int bshift, uint32_t 
     const uint32_t bucket = bshift >= 64 ? 0u : (uint32_t)(h >> bshift);
     if (SCATTER) {
         const uint32_t pos = atomicAdd(&counters[bucket], 1u);
-        uint4 *dst = reinterpret_cast<uint4 *>(part + pos);
-        stg128(dst, make_uint4((uint32_t)r.a, (uint32_t)(r.a >> 32), (uint32_t)r.b, (uint32_t)(r.b >> 32)));
-        stg128(dst + 1, make_uint4((uint32_t)r.value, (uint32_t)(r.value >> 32), r.t, r.proto));
+        stg256(part + pos, make_uint4((uint32_t)r.a, (uint32_t)(r.a >> 32), (uint32_t)r.b, (uint32_t)(r.b >> 32)),
+               make_uint4((uint32_t)r.value, (uint32_t)(r.value >> 32), r.t, r.proto));
     } else {
         atomicAdd(&counters[bucket], 1u);
     }
@@ -151,8 +152,26 @@ __global__ void __launch_bounds__(256) partition_kernel(ColPtrs c, uint64_t R, R
                 r[i].value = pack64(vlo[i], vhi[i]);
                 r[i].keep = row_keep(f, c, base + i, fsv[i], fev[i]);
             }
+            if (SCATTER) {
+                // all eight cursor atomics in flight before the first dependent store
+                uint32_t pos[8];
 #pragma unroll
-            for (int i = 0; i < 8; i++) emit_row<SCATTER>(r[i], bshift, counters, part);
+                for (int i = 0; i < 8; i++) {
+                    const uint64_t h = key_hash(r[i].a, r[i].b, r[i].proto);
+                    const uint32_t bucket = bshift >= 64 ? 0u : (uint32_t)(h >> bshift);
+                    pos[i] = r[i].keep ? atomicAdd(&counters[bucket], 1u) : 0xffffffffu;
+                }
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    if (pos[i] != 0xffffffffu)
+                        stg256(part + pos[i],
+                               make_uint4((uint32_t)r[i].a, (uint32_t)(r[i].a >> 32), (uint32_t)r[i].b, (uint32_t)(r[i].b >> 32)),
+                               make_uint4((uint32_t)r[i].value, (uint32_t)(r[i].value >> 32), r[i].t, r[i].proto));
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; i++) emit_row<SCATTER>(r[i], bshift, counters, part);
+            }
         } else {
             const uint64_t end = base + 8 < R ? base + 8 : R;
             for (uint64_t i = base; i < end; i++) {
@@ -165,8 +184,16 @@ __global__ void __launch_bounds__(256) partition_kernel(ColPtrs c, uint64_t R, R
 }
 
 // ----------------------------------------------------------------------------------------
-// single-CTA exclusive scans (bucket offsets; series base per bucket)
+// multi-CTA exclusive scans (bucket offsets; series base per bucket).  The grid never exceeds the
+// SM count with one 1024-thread CTA each, so all CTAs are co-resident and a CTA may spin on the
+// partial sums its lower-numbered peers publish (flags carry a per-launch epoch: no memset).
 // ----------------------------------------------------------------------------------------
+constexpr int kScanMaxCtas = 128;
+struct ScanSync {                       // lives in global memory, zero-initialised once
+    unsigned long long part[kScanMaxCtas][4];
+    unsigned int flag[kScanMaxCtas];
+};
+
 __device__ __forceinline__ uint32_t block_exclusive_scan_1024(uint32_t v, uint32_t *total)
 {
     __shared__ uint32_t warp_sums[32];
@@ -177,6 +204,7 @@ __device__ __forceinline__ uint32_t block_exclusive_scan_1024(uint32_t v, uint32
         uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
         if (lane >= d) inc += o;
     }
+    __syncthreads();                    // protects warp_sums across back-to-back calls
     if (lane == 31) warp_sums[warp] = inc;
     __syncthreads();
     if (warp == 0) {
@@ -194,18 +222,54 @@ __device__ __forceinline__ uint32_t block_exclusive_scan_1024(uint32_t v, uint32
     return warp_sums[warp] + inc - v;
 }
 
+// publish this CTA's totals, then sum the totals of all lower CTAs (and of all CTAs)
+__device__ __forceinline__ void grid_prefix(ScanSync *sy, uint32_t epoch, const unsigned long long mine[4],
+                                            unsigned long long before[4], unsigned long long all[4])
+{
+    __shared__ unsigned long long sh_before[4], sh_all[4];
+    const uint32_t c = blockIdx.x, G = gridDim.x;
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < 4; k++) sy->part[c][k] = mine[k];
+        __threadfence();
+        atomicExch(&sy->flag[c], epoch);
+    }
+    if (threadIdx.x < 32) {
+        unsigned long long b[4] = {0, 0, 0, 0}, a[4] = {0, 0, 0, 0};
+        for (uint32_t o = threadIdx.x; o < G; o += 32) {
+            while (atomicAdd(&sy->flag[o], 0u) != epoch) { }
+            __threadfence();
+            for (int k = 0; k < 4; k++) {
+                const unsigned long long x = *reinterpret_cast<volatile unsigned long long *>(&sy->part[o][k]);
+                a[k] += x;
+                if (o < c) b[k] += x;
+            }
+        }
+        for (int k = 0; k < 4; k++) {
+            for (int d = 16; d; d >>= 1) {
+                b[k] += __shfl_xor_sync(0xffffffffu, b[k], d);
+                a[k] += __shfl_xor_sync(0xffffffffu, a[k], d);
+            }
+        }
+        if (threadIdx.x == 0)
+            for (int k = 0; k < 4; k++) { sh_before[k] = b[k]; sh_all[k] = a[k]; }
+    }
+    __syncthreads();
+    for (int k = 0; k < 4; k++) { before[k] = sh_before[k]; all[k] = sh_all[k]; }
+}
+
 // offsets[B+1] = exclusive scan of hist; cursor = copy of offsets; lists the buckets larger
 // than `cap` in ascending bucket order together with the exclusive scan of their sizes
 // (big_base[n_big+1]) -- the spill path relies on that order.
 __global__ void __launch_bounds__(1024) bucket_scan_kernel(const uint32_t *__restrict__ hist, uint32_t *__restrict__ offsets,
                                                            uint32_t *__restrict__ cursor, uint32_t B, uint32_t cap,
                                                            uint32_t *__restrict__ big_list, uint32_t *__restrict__ big_base,
-                                                           uint32_t *__restrict__ stats)
+                                                           uint32_t *__restrict__ stats, ScanSync *sy, uint32_t epoch)
 {
     __shared__ uint32_t total_s, nbig_s, bigrows_s, maxb_s;
     if (threadIdx.x == 0) maxb_s = 0;
-    const uint32_t per = (B + 1023) / 1024;
-    const uint32_t lo = min(B, threadIdx.x * per), hi = min(B, lo + per);
+    const uint32_t per = (B + gridDim.x * 1024 - 1) / (gridDim.x * 1024);
+    const uint32_t first = (blockIdx.x * 1024 + threadIdx.x) * per;
+    const uint32_t lo = min(B, first), hi = min(B, first + per);
     uint32_t sum = 0, nbig = 0, bigrows = 0, mx = 0;
     for (uint32_t i = lo; i < hi; i++) {
         const uint32_t h = hist[i];
@@ -214,11 +278,14 @@ __global__ void __launch_bounds__(1024) bucket_scan_kernel(const uint32_t *__res
         if (h > cap) { nbig++; bigrows += h; }
     }
     const uint32_t pre = block_exclusive_scan_1024(sum, &total_s);
-    __syncthreads();
     const uint32_t pre_nbig = block_exclusive_scan_1024(nbig, &nbig_s);
-    __syncthreads();
     const uint32_t pre_rows = block_exclusive_scan_1024(bigrows, &bigrows_s);
-    uint32_t run = pre, k = pre_nbig, br = pre_rows;
+    atomicMax(&maxb_s, mx);
+    __syncthreads();
+    const unsigned long long mine[4] = {total_s, nbig_s, bigrows_s, maxb_s};
+    unsigned long long before[4], all[4];
+    grid_prefix(sy, epoch, mine, before, all);
+    uint32_t run = (uint32_t)before[0] + pre, k = (uint32_t)before[1] + pre_nbig, br = (uint32_t)before[2] + pre_rows;
     for (uint32_t i = lo; i < hi; i++) {
         const uint32_t h = hist[i];
         offsets[i] = run;
@@ -231,39 +298,43 @@ __global__ void __launch_bounds__(1024) bucket_scan_kernel(const uint32_t *__res
             br += h;
         }
     }
-    atomicMax(&maxb_s, mx);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        offsets[B] = total_s;
-        big_base[nbig_s] = bigrows_s;
-        stats[ST_KEPT] = total_s;
-        stats[ST_NBIG] = nbig_s;
-        stats[ST_BIGROWS] = bigrows_s;
-        stats[ST_MAXBUCKET] = maxb_s;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        offsets[B] = (uint32_t)all[0];
+        big_base[all[1]] = (uint32_t)all[2];
+        stats[ST_KEPT] = (uint32_t)all[0];
+        stats[ST_NBIG] = (uint32_t)all[1];
+        stats[ST_BIGROWS] = (uint32_t)all[2];
     }
+    if (threadIdx.x == 0) atomicMax(&stats[ST_MAXBUCKET], maxb_s);
 }
 
 // sbase[B+1] = exclusive scan of series-per-bucket; also totals points.
 __global__ void __launch_bounds__(1024) series_scan_kernel(const uint32_t *__restrict__ nsb, const uint32_t *__restrict__ npb,
-                                                           uint32_t *__restrict__ sbase, uint32_t B, uint32_t *__restrict__ stats)
+                                                           uint32_t *__restrict__ sbase, uint32_t B, uint32_t *__restrict__ stats,
+                                                           ScanSync *sy, uint32_t epoch)
 {
     __shared__ uint32_t total_s;
     __shared__ unsigned long long points_s;
     if (threadIdx.x == 0) points_s = 0;
-    const uint32_t per = (B + 1023) / 1024;
-    const uint32_t lo = min(B, threadIdx.x * per), hi = min(B, lo + per);
+    __syncthreads();
+    const uint32_t per = (B + gridDim.x * 1024 - 1) / (gridDim.x * 1024);
+    const uint32_t first = (blockIdx.x * 1024 + threadIdx.x) * per;
+    const uint32_t lo = min(B, first), hi = min(B, first + per);
     uint32_t sum = 0;
     unsigned long long pts = 0;
     for (uint32_t i = lo; i < hi; i++) { sum += nsb[i]; pts += npb[i]; }
     const uint32_t pre = block_exclusive_scan_1024(sum, &total_s);
-    uint32_t run = pre;
-    for (uint32_t i = lo; i < hi; i++) { sbase[i] = run; run += nsb[i]; }
-    atomicAdd(&points_s, pts);
+    if (pts) atomicAdd(&points_s, pts);
     __syncthreads();
-    if (threadIdx.x == 0) {
-        sbase[B] = total_s;
-        stats[ST_SERIES] = total_s;
-        stats[ST_POINTS] = (uint32_t)points_s;
+    const unsigned long long mine[4] = {total_s, points_s, 0, 0};
+    unsigned long long before[4], all[4];
+    grid_prefix(sy, epoch, mine, before, all);
+    uint32_t run = (uint32_t)before[0] + pre;
+    for (uint32_t i = lo; i < hi; i++) { sbase[i] = run; run += nsb[i]; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        sbase[B] = (uint32_t)all[0];
+        stats[ST_SERIES] = (uint32_t)all[0];
+        stats[ST_POINTS] = (uint32_t)all[1];
     }
 }
 
@@ -309,8 +380,45 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *w
     return warp_sums[warp] + inc - v;
 }
 
+
+// Number of elements of a[lo, hi) that are < lim.  `a` is a 16-byte aligned shared-memory array;
+// the body reads four elements per LDS.128 (lanes of one series read the same address -> broadcast).
+__device__ __forceinline__ uint32_t count_lt_u32(const uint32_t *a, uint32_t lo, uint32_t hi, uint32_t lim)
+{
+    uint32_t c = 0, i = lo;
+    const uint32_t head_end = min(hi, (lo + 3u) & ~3u);
+    for (; i < head_end; i++) c += a[i] < lim ? 1u : 0u;
+    const uint32_t body_end = i + ((hi - i) & ~3u);
+#pragma unroll 2
+    for (; i < body_end; i += 4) {
+        const uint4 q = *reinterpret_cast<const uint4 *>(a + i);
+        c += q.x < lim ? 1u : 0u;
+        c += q.y < lim ? 1u : 0u;
+        c += q.z < lim ? 1u : 0u;
+        c += q.w < lim ? 1u : 0u;
+    }
+    for (; i < hi; i++) c += a[i] < lim ? 1u : 0u;
+    return c;
+}
+__device__ __forceinline__ uint32_t count_lt_u64(const unsigned long long *a, uint32_t lo, uint32_t hi, unsigned long long lim)
+{
+    uint32_t c = 0, i = lo;
+    const uint32_t head_end = min(hi, (lo + 1u) & ~1u);
+    for (; i < head_end; i++) c += a[i] < lim ? 1u : 0u;
+    const uint32_t body_end = i + ((hi - i) & ~1u);
+#pragma unroll 4
+    for (; i < body_end; i += 2) {
+        const ulonglong2 q = *reinterpret_cast<const ulonglong2 *>(a + i);
+        c += q.x < lim ? 1u : 0u;
+        c += q.y < lim ? 1u : 0u;
+    }
+    for (; i < hi; i++) c += a[i] < lim ? 1u : 0u;
+    return c;
+}
+
 template <int CAP, int NT, bool VRANK>
-__global__ void __launch_bounds__(NT) group_kernel(Row32 *__restrict__ part, const uint32_t *__restrict__ offsets, int sshift,
+__global__ void __launch_bounds__(NT) group_kernel(Row32 *__restrict__ part, const uint32_t *__restrict__ offsets,
+                                                   uint32_t lo_rows, int sshift,
                                                    uint64_t *__restrict__ csr_v, uint32_t *__restrict__ csr_t,
                                                    uint32_t *__restrict__ csr_p, uint32_t *__restrict__ nsb,
                                                    uint32_t *__restrict__ npb, int reducer)
@@ -326,10 +434,7 @@ __global__ void __launch_bounds__(NT) group_kernel(Row32 *__restrict__ part, con
     const uint32_t off_b = offsets[bkt];
     const uint32_t n = offsets[bkt + 1] - off_b;
     const int tid = threadIdx.x;
-    if (n == 0 || n > (uint32_t)CAP) {          // empty, or oversized -> spill path owns it
-        if (tid == 0 && n == 0) { nsb[bkt] = 0; npb[bkt] = 0; }
-        return;
-    }
+    if (n <= lo_rows || n > (uint32_t)CAP) return;   // another capacity class (or the spill path) owns it
 
     // ---- L: one TMA bulk copy of the whole bucket into shared memory -----------------
     const uint32_t bar = smem_u32(&s.mbar);
@@ -447,13 +552,9 @@ __global__ void __launch_bounds__(NT) group_kernel(Row32 *__restrict__ part, con
             const uint32_t slot = mySP[j] & 0xffffu, pos = mySP[j] >> 16;
             const uint32_t so = s.soff[slot], cnt = s.ht[slot] >> 16;
             const uint32_t t = myT[j];
-            uint32_t rank = 0;
-            const uint32_t *tsr = ts + so;
-#pragma unroll 4
-            for (uint32_t q = 0; q < cnt; q++) {
-                const uint32_t tq = tsr[q];
-                rank += (tq < t || (tq == t && q < pos)) ? 1u : 0u;
-            }
+            // rank = #{q < pos : t_q <= t} + #{q > pos : t_q < t}   (stable by arrival order)
+            uint32_t rank = (t == 0xffffffffu) ? pos : count_lt_u32(ts, so, so + pos, t + 1u);
+            rank += count_lt_u32(ts, so + pos, so + cnt, t);
             tout[so + rank] = t;
             vout[so + rank] = myV[j];
             if (VRANK) pslot[so + rank] = (uint16_t)slot;
@@ -511,13 +612,8 @@ __global__ void __launch_bounds__(NT) group_kernel(Row32 *__restrict__ part, con
             const uint32_t so = s.soff[slot], cnt = s.ht[slot] >> 16, me = p - so;
             if (me >= cnt) continue;                    // hole left by the duplicate reduce
             const unsigned long long v = vout[p];
-            const unsigned long long *vs = vout + so;
-            uint32_t rank = 0;
-#pragma unroll 4
-            for (uint32_t q = 0; q < cnt; q++) {
-                const unsigned long long vq = vs[q];
-                rank += (vq < v || (vq == v && q < me)) ? 1u : 0u;
-            }
+            uint32_t rank = (v == ~0ull) ? me : count_lt_u64(vout, so, so + me, v + 1ull);
+            rank += count_lt_u64(vout, so + me, so + cnt, v);
             pout[so + rank] = (uint16_t)me;
         }
         __syncthreads();
@@ -562,19 +658,36 @@ __device__ __forceinline__ void write_out(const OutCols &o, uint32_t idx, const 
     o.anomaly[idx] = flag ? 1 : 0;
 }
 
+// Visit v[0..n) in order.  `v` points into csr_v (8-byte elements, base 256-byte aligned); after a
+// scalar head the loop reads one full 32-byte sector (four values) per step with two 128-bit loads,
+// so a thread walking its own series never fetches a sector twice.
+template <class F>
+__device__ __forceinline__ void for_each_value(const uint64_t *__restrict__ v, uint32_t n, F &&f)
+{
+    uint32_t i = 0;
+    const uint32_t mis = (uint32_t)((reinterpret_cast<uintptr_t>(v) >> 3) & 3u);
+    const uint32_t head = min(n, (4u - mis) & 3u);
+    for (; i < head; i++) f(v[i], i);
+    for (; i + 4 <= n; i += 4) {
+        const ulonglong2 a = *reinterpret_cast<const ulonglong2 *>(v + i);
+        const ulonglong2 b = *reinterpret_cast<const ulonglong2 *>(v + i + 2);
+        f(a.x, i); f(a.y, i + 1); f(b.x, i + 2); f(b.y, i + 3);
+    }
+    for (; i < n; i++) f(v[i], i);
+}
+
 // stddev_samp as Spark's CentralMomentAgg computes it (Welford), sequential in time order.
 __device__ __forceinline__ double series_stddev(const uint64_t *__restrict__ v, uint32_t n, bool &has_sd)
 {
     double cnt = 0.0, avg = 0.0, m2 = 0.0;
-#pragma unroll 4
-    for (uint32_t i = 0; i < n; i++) {
-        const double x = __ull2double_rn(v[i]);
+    for_each_value(v, n, [&](uint64_t raw, uint32_t) {
+        const double x = __ull2double_rn(raw);
         cnt = __dadd_rn(cnt, 1.0);
         const double d = __dsub_rn(x, avg);
         const double dn = __ddiv_rn(d, cnt);
         avg = __dadd_rn(avg, dn);
         m2 = __dadd_rn(m2, __dmul_rn(d, __dsub_rn(d, dn)));
-    }
+    });
     has_sd = n >= 2;
     return has_sd ? __dsqrt_rn(__ddiv_rn(m2, __dsub_rn(cnt, 1.0))) : __longlong_as_double(0x7ff8000000000000LL);
 }
@@ -605,12 +718,11 @@ __global__ void __launch_bounds__(NT) detect_ewma_kernel(const Row32 *__restrict
             count = e.n;
         } else if (has_sd) {
             double prev = 0.0;
-#pragma unroll 4
-            for (uint32_t q = 0; q < e.n; q++) {
-                const double x = __ull2double_rn(v[q]);
+            for_each_value(v, e.n, [&](uint64_t raw, uint32_t) {
+                const double x = __ull2double_rn(raw);
                 prev = __dadd_rn(__dmul_rn(0.5, prev), __dmul_rn(0.5, x));
                 count += (fabs(__dsub_rn(x, prev)) > sd) ? 1u : 0u;
-            }
+            });
         }
     }
     const uint32_t pre = block_exclusive_scan<NT>(count, warp_sums, &total_s);
@@ -620,15 +732,15 @@ __global__ void __launch_bounds__(NT) detect_ewma_kernel(const Row32 *__restrict
     uint32_t idx = base_s + pre;
     const uint32_t *t = csr_t + e.off;
     double prev = 0.0;
-    for (uint32_t q = 0; q < e.n; q++) {
-        const double x = __ull2double_rn(v[q]);
+    for_each_value(v, e.n, [&](uint64_t raw, uint32_t q) {
+        const double x = __ull2double_rn(raw);
         prev = __dadd_rn(__dmul_rn(0.5, prev), __dmul_rn(0.5, x));
         const bool flag = has_sd && (fabs(__dsub_rn(x, prev)) > sd);
         if (flag || emit_all) {
             if (idx < out_cap) write_out(out, idx, e, t[q], sd, prev, x, flag);
             idx++;
         }
-    }
+    });
 }
 
 // ----------------------------------------------------------------------------------------
@@ -795,39 +907,66 @@ cudaError_t launch_scatter(cudaStream_t st, const ColPtrs &c, uint64_t R, const 
     return cudaGetLastError();
 }
 
-cudaError_t launch_bucket_scan(cudaStream_t st, const uint32_t *hist, uint32_t *offsets, uint32_t *cursor, uint32_t B,
-                               uint32_t cap, uint32_t *big_list, uint32_t *big_base, uint32_t *stats)
+size_t scan_sync_bytes() { return sizeof(ScanSync); }
+
+static uint32_t scan_grid(uint32_t B)
 {
-    bucket_scan_kernel<<<1, 1024, 0, st>>>(hist, offsets, cursor, B, cap, big_list, big_base, stats);
+    uint32_t g = (B + 1023) / 1024;
+    const uint32_t cap = (uint32_t)min(kScanMaxCtas, num_sms() - 4);     // all CTAs must be co-resident
+    return g < 1 ? 1 : (g > cap ? cap : g);
+}
+
+cudaError_t launch_bucket_scan(cudaStream_t st, const uint32_t *hist, uint32_t *offsets, uint32_t *cursor, uint32_t B,
+                               uint32_t cap, uint32_t *big_list, uint32_t *big_base, uint32_t *stats, void *scan_sync,
+                               uint32_t epoch)
+{
+    bucket_scan_kernel<<<scan_grid(B), 1024, 0, st>>>(hist, offsets, cursor, B, cap, big_list, big_base, stats,
+                                                     static_cast<ScanSync *>(scan_sync), epoch);
     return cudaGetLastError();
 }
 
-cudaError_t launch_group(cudaStream_t st, Row32 *part, const uint32_t *offsets, uint32_t B, int logB, uint64_t *csr_v,
-                         uint32_t *csr_t, uint32_t *csr_p, uint32_t *nsb, uint32_t *npb, int reducer)
+template <int CAP, bool VRANK>
+static cudaError_t launch_group_class(cudaStream_t st, Row32 *part, const uint32_t *offsets, uint32_t B, uint32_t lo_rows,
+                                      int sshift, uint64_t *csr_v, uint32_t *csr_t, uint32_t *csr_p, uint32_t *nsb,
+                                      uint32_t *npb, int reducer)
 {
-    using S = GroupSmem<kGroupCap, kGroupThreads>;
+    using S = GroupSmem<CAP, kGroupThreads>;
     static bool configured = false;
-    auto kern = group_kernel<kGroupCap, kGroupThreads, false>;
-    auto kern_v = group_kernel<kGroupCap, kGroupThreads, true>;
+    auto kern = group_kernel<CAP, kGroupThreads, VRANK>;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(S));
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(kern_v, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(S));
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    int sshift = 64 - logB - 12;          // 12 hash bits below the bucket bits pick the slot
-    if (sshift < 0) sshift = 0;
-    if (csr_p)
-        kern_v<<<B, kGroupThreads, sizeof(S), st>>>(part, offsets, sshift, csr_v, csr_t, csr_p, nsb, npb, reducer);
-    else
-        kern<<<B, kGroupThreads, sizeof(S), st>>>(part, offsets, sshift, csr_v, csr_t, csr_p, nsb, npb, reducer);
+    kern<<<B, kGroupThreads, sizeof(S), st>>>(part, offsets, lo_rows, sshift, csr_v, csr_t, csr_p, nsb, npb, reducer);
     return cudaGetLastError();
 }
 
-cudaError_t launch_series_scan(cudaStream_t st, const uint32_t *nsb, const uint32_t *npb, uint32_t *sbase, uint32_t B,
-                               uint32_t *stats)
+// Two shared-memory capacity classes: most buckets hold <= kGroupCapSmall rows and run at a higher
+// occupancy; the rest (up to kGroupCap rows) use the big configuration.  Empty buckets keep the
+// zeroes the caller memset into nsb / npb.
+cudaError_t launch_group(cudaStream_t st, Row32 *part, const uint32_t *offsets, uint32_t B, int logB, uint64_t *csr_v,
+                         uint32_t *csr_t, uint32_t *csr_p, uint32_t *nsb, uint32_t *npb, int reducer)
 {
-    series_scan_kernel<<<1, 1024, 0, st>>>(nsb, npb, sbase, B, stats);
+    int sshift = 64 - logB - 12;          // 12 hash bits below the bucket bits pick the slot
+    if (sshift < 0) sshift = 0;
+    cudaError_t e;
+    if (csr_p) {
+        e = launch_group_class<kGroupCapSmall, true>(st, part, offsets, B, 0, sshift, csr_v, csr_t, csr_p, nsb, npb, reducer);
+        if (e == cudaSuccess)
+            e = launch_group_class<kGroupCap, true>(st, part, offsets, B, kGroupCapSmall, sshift, csr_v, csr_t, csr_p, nsb, npb, reducer);
+    } else {
+        e = launch_group_class<kGroupCapSmall, false>(st, part, offsets, B, 0, sshift, csr_v, csr_t, csr_p, nsb, npb, reducer);
+        if (e == cudaSuccess)
+            e = launch_group_class<kGroupCap, false>(st, part, offsets, B, kGroupCapSmall, sshift, csr_v, csr_t, csr_p, nsb, npb, reducer);
+    }
+    return e;
+}
+
+cudaError_t launch_series_scan(cudaStream_t st, const uint32_t *nsb, const uint32_t *npb, uint32_t *sbase, uint32_t B,
+                               uint32_t *stats, void *scan_sync, uint32_t epoch)
+{
+    series_scan_kernel<<<scan_grid(B), 1024, 0, st>>>(nsb, npb, sbase, B, stats, static_cast<ScanSync *>(scan_sync), epoch);
     return cudaGetLastError();
 }
 
