@@ -46,6 +46,16 @@ struct RowFilter {
     const uint32_t *ns_ignore;       // device pointer
 };
 
+// A bucket's rows may arrive as several segments: one per source rank after the multi-GPU exchange
+// (one segment, the local partition buffer itself, on a single GPU).  Segment r holds the rows of
+// this rank's bucket range in bucket order; off[r] is the exclusive row offset of every bucket in it.
+constexpr int kMaxSeg = 8;
+struct SegDesc {
+    const Row32 *base[kMaxSeg];
+    const uint32_t *off[kMaxSeg];
+    int nseg;
+};
+
 struct OutCols {
     uint32_t *src_ip, *dst_ip, *flow_start, *flow_end;
     uint16_t *src_port, *dst_port;

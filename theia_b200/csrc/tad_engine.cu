@@ -69,7 +69,8 @@ struct tad_ctx {
     int num_sms = 148;
     // device workspace (grow-only, reused across jobs; jobs are serialized by the worker)
     DevBuf d_col[10], hist, offsets, cursor, big_list, big_base, csr_p, stats, part, csr_v, csr_t, nsb, npb, sbase, outb, ns_ignore, spill,
-        dbx, dbi, exch, scan_sync;
+        dbx, dbi, exch, scan_sync, small, hist_all, seg_off, seg_total, entries;
+    unsigned long long *h_small = nullptr;   // pinned, 64 x u64
     uint32_t scan_epoch = 0;
     uint32_t *h_stats = nullptr;   // pinned readback of the device scalars
     std::mutex pool_mu;
@@ -291,65 +292,140 @@ void run_job(tad_ctx *ctx, tad_job *job)
     }
 
     // ---- partition -------------------------------------------------------------------------
-    const int logB = pick_logb(ctx, R);
-    const uint32_t B = 1u << logB;
+    const int world = ctx->cfg.world_size, me = ctx->cfg.rank;
+    uint64_t R_total = R;
+    ensure(ctx->small, 4096);
+    unsigned long long *d_small = static_cast<unsigned long long *>(ctx->small.p);
+    if (world > 1) {
+        // global row count -> same bucket count on every rank
+        ctx->h_small[0] = R;
+        CU(cudaMemcpyAsync(d_small, ctx->h_small, 8, cudaMemcpyHostToDevice, st));
+        if (nccl_allgather(&ctx->nccl, d_small, d_small + 8, 8, st)) fail(TAD_ERR_NCCL, "%s", nccl_last_error());
+        CU(cudaMemcpyAsync(ctx->h_small, d_small + 8, 8 * world, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        R_total = 0;
+        for (int r = 0; r < world; r++) R_total += ctx->h_small[r];
+    }
+    int logB = pick_logb(ctx, R_total);
+    int logW = 0;
+    while ((1 << logW) < world) logW++;
+    if (logB < logW) logB = logW;
+    const uint32_t B = 1u << logB;                 // global buckets
+    const uint32_t Bl = B >> logW;                 // buckets owned by one rank
+    const uint32_t b_lo = Bl * (uint32_t)me;
     ensure(ctx->hist, (size_t)B * 4);
     ensure(ctx->offsets, ((size_t)B + 1) * 4);
     ensure(ctx->cursor, (size_t)B * 4);
     ensure(ctx->big_list, (size_t)B * 4);
     ensure(ctx->big_base, ((size_t)B + 1) * 4);
-    ensure(ctx->nsb, (size_t)B * 4);
-    ensure(ctx->npb, (size_t)B * 4);
-    ensure(ctx->sbase, ((size_t)B + 1) * 4);
+    ensure(ctx->nsb, (size_t)Bl * 4);
+    ensure(ctx->npb, (size_t)Bl * 4);
+    ensure(ctx->sbase, ((size_t)Bl + 1) * 4);
     ensure(ctx->part, (R ? R : 1) * sizeof(Row32));
-    ensure(ctx->csr_v, (R ? R : 1) * 8);
-    ensure(ctx->csr_t, (R ? R : 1) * 4);
     uint32_t *hist = (uint32_t *)ctx->hist.p, *offsets = (uint32_t *)ctx->offsets.p, *cursor = (uint32_t *)ctx->cursor.p;
     uint32_t *big_base = (uint32_t *)ctx->big_base.p;
     uint32_t *big_list = (uint32_t *)ctx->big_list.p, *nsb = (uint32_t *)ctx->nsb.p, *npb = (uint32_t *)ctx->npb.p;
     uint32_t *sbase = (uint32_t *)ctx->sbase.p;
     Row32 *part = (Row32 *)ctx->part.p;
-    uint64_t *csr_v = (uint64_t *)ctx->csr_v.p;
-    uint32_t *csr_t = (uint32_t *)ctx->csr_t.p;
 
     CU(cudaMemsetAsync(hist, 0, (size_t)B * 4, st));
-    CU(cudaMemsetAsync(nsb, 0, (size_t)B * 4, st));
-    CU(cudaMemsetAsync(npb, 0, (size_t)B * 4, st));
+    CU(cudaMemsetAsync(nsb, 0, (size_t)Bl * 4, st));
+    CU(cudaMemsetAsync(npb, 0, (size_t)Bl * 4, st));
     mark(-1);
     CU(launch_hist(st, c, R, f, logB, hist)); launches += R ? 1 : 0;
     mark(TAD_PHASE_HIST);
-    CU(launch_bucket_scan(st, hist, offsets, cursor, B, kGroupCap, big_list, big_base, d_stats, ctx->scan_sync.p,
-                          ++ctx->scan_epoch)); launches++;
+    // single GPU: these are the final bucket offsets; multi GPU: offsets inside the local send buffer
+    CU(launch_bucket_scan(st, hist, offsets, cursor, B, world > 1 ? 0xffffffffu : (uint32_t)kGroupCap, big_list, big_base,
+                          d_stats, ctx->scan_sync.p, ++ctx->scan_epoch)); launches++;
     mark(TAD_PHASE_SCAN);
     CU(launch_scatter(st, c, R, f, logB, cursor, part)); launches += R ? 1 : 0;
     mark(TAD_PHASE_SCATTER);
-    CU(cudaMemcpyAsync(ctx->h_stats, d_stats, ST_COUNT * 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+
+    SegDesc seg{};
+    SeriesEntry *entries = nullptr;
+    uint64_t kept = 0, owned = 0;
+    if (world == 1) {
+        CU(cudaMemcpyAsync(ctx->h_stats, d_stats, ST_COUNT * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        kept = owned = ctx->h_stats[ST_KEPT];
+        seg.nseg = 1;
+        seg.base[0] = part;
+        seg.off[0] = offsets;
+        entries = reinterpret_cast<SeriesEntry *>(part);      // in place over the staged bucket rows
+    } else {
+        // ---- exchange: one all-gather of the histograms + one all-to-all-v of packed rows -----------
+        mark(-1);
+        ensure(ctx->hist_all, (size_t)B * 4 * world);
+        ensure(ctx->seg_off, ((size_t)Bl + 1) * 4 * world);
+        ensure(ctx->seg_total, (size_t)Bl * 4);
+        uint32_t *hist_all = (uint32_t *)ctx->hist_all.p, *seg_off = (uint32_t *)ctx->seg_off.p;
+        uint32_t *seg_total = (uint32_t *)ctx->seg_total.p;
+        if (nccl_allgather(&ctx->nccl, hist, hist_all, (size_t)B * 4, st)) fail(TAD_ERR_NCCL, "%s", nccl_last_error());
+        CU(launch_segment_scan(st, hist_all, B, b_lo, Bl, world, seg_off, seg_total, d_small)); launches += 2;
+        // rows this rank sends to rank p = offsets[(p+1)*Bl] - offsets[p*Bl]
+        CU(cudaMemcpy2DAsync(ctx->h_small + 16, 8, offsets, (size_t)Bl * 4, 4, world + 1, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(ctx->h_small, d_small, 8 * world, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(ctx->h_stats, d_stats, ST_COUNT * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        check_cancel();
+        kept = ctx->h_stats[ST_KEPT];
+        uint64_t send_off[kMaxSeg], send_bytes[kMaxSeg], recv_off[kMaxSeg], recv_bytes[kMaxSeg], recv_total = 0;
+        for (int p = 0; p < world; p++) {
+            const uint32_t lo = (uint32_t)ctx->h_small[16 + p], hi = (uint32_t)ctx->h_small[16 + p + 1];
+            send_off[p] = (uint64_t)lo * 32;
+            send_bytes[p] = (uint64_t)(hi - lo) * 32;
+            recv_bytes[p] = ctx->h_small[p] * 32;
+            recv_off[p] = recv_total;
+            if (p != me) recv_total += recv_bytes[p];
+            owned += ctx->h_small[p];
+        }
+        if (owned >= (1ull << 32) - 1) fail(TAD_ERR_INVALID_ARG, "more than 2^32-2 rows owned by one GPU after the exchange");
+        ensure(ctx->exch, recv_total ? recv_total : 32);
+        if (nccl_alltoallv(&ctx->nccl, part, send_off, send_bytes, ctx->exch.p, recv_off, recv_bytes, st))
+            fail(TAD_ERR_NCCL, "%s", nccl_last_error());
+        seg.nseg = world;
+        for (int p = 0; p < world; p++) {
+            seg.base[p] = p == me ? part + (send_off[me] / 32) : reinterpret_cast<const Row32 *>((const char *)ctx->exch.p + recv_off[p]);
+            seg.off[p] = seg_off + (size_t)p * (Bl + 1);
+        }
+        // final (virtual) bucket offsets of the owned range, oversized-bucket list
+        CU(launch_bucket_scan(st, seg_total, offsets, cursor, Bl, kGroupCap, big_list, big_base, d_stats, ctx->scan_sync.p,
+                              ++ctx->scan_epoch)); launches++;
+        mark(TAD_PHASE_EXCHANGE);
+        CU(cudaMemcpyAsync(ctx->h_stats, d_stats, ST_COUNT * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        ensure(ctx->entries, (owned ? owned : 1) * sizeof(SeriesEntry));
+        entries = static_cast<SeriesEntry *>(ctx->entries.p);
+    }
     check_cancel();
-    const uint64_t kept = ctx->h_stats[ST_KEPT];
     const uint32_t n_big = ctx->h_stats[ST_NBIG];
     const uint64_t big_rows = ctx->h_stats[ST_BIGROWS];
-    set_progress(job, TAD_STATE_RUNNING, 3);    // ingest, partition, exchange (single GPU: no-op)
+    set_progress(job, TAD_STATE_RUNNING, 3);    // ingest, partition, exchange
 
     // ---- group ------------------------------------------------------------------------------
+    const uint64_t cap_rows = owned ? owned : 1;
+    ensure(ctx->csr_v, cap_rows * 8);
+    ensure(ctx->csr_t, cap_rows * 4);
+    uint64_t *csr_v = (uint64_t *)ctx->csr_v.p;
+    uint32_t *csr_t = (uint32_t *)ctx->csr_t.p;
     uint32_t *csr_p = nullptr;
     if (sp.algo == TAD_ALGO_DBSCAN) {
-        ensure(ctx->csr_p, (R ? R : 1) * 4);
+        ensure(ctx->csr_p, cap_rows * 4);
         csr_p = (uint32_t *)ctx->csr_p.p;
     }
     mark(-1);
-    CU(launch_group(st, part, offsets, B, logB, csr_v, csr_t, csr_p, nsb, npb, sp.reducer)); launches += 2;
+    CU(launch_group(st, seg, entries, offsets, Bl, logB, csr_v, csr_t, csr_p, nsb, npb, sp.reducer)); launches += 2;
     mark(TAD_PHASE_GROUP);
     if (n_big) {
         const size_t need = spill_scratch_bytes(big_rows);
         ensure(ctx->spill, need);
         int l = 0;
-        CU(run_spill(st, part, offsets, big_list, big_base, n_big, big_rows, ctx->spill.p, ctx->spill.cap, csr_v, csr_t, nsb,
-                     npb, sp.reducer, &l));
+        CU(run_spill(st, seg, entries, offsets, big_list, big_base, n_big, big_rows, ctx->spill.p, ctx->spill.cap, csr_v, csr_t,
+                     nsb, npb, sp.reducer, &l));
         launches += l;
         mark(TAD_PHASE_SPILL);
     }
-    CU(launch_series_scan(st, nsb, npb, sbase, B, d_stats, ctx->scan_sync.p, ++ctx->scan_epoch)); launches++;
+    CU(launch_series_scan(st, nsb, npb, sbase, Bl, d_stats, ctx->scan_sync.p, ++ctx->scan_epoch)); launches++;
     CU(cudaMemcpyAsync(ctx->h_stats, d_stats, ST_COUNT * 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     check_cancel();
@@ -372,12 +448,12 @@ void run_job(tad_ctx *ctx, tad_job *job)
         CU(cudaMemsetAsync(d_stats + ST_OUTCOUNT, 0, 4, st));
         mark(-1);
         if (sp.algo == TAD_ALGO_EWMA) {
-            CU(launch_detect_ewma(st, part, offsets, sbase, B, S, csr_v, csr_t, oc, (uint32_t)out_cap, d_stats, emit_all));
+            CU(launch_detect_ewma(st, entries, offsets, sbase, Bl, S, csr_v, csr_t, oc, (uint32_t)out_cap, d_stats, emit_all));
             launches += S ? 1 : 0;
         } else if (sp.algo == TAD_ALGO_DBSCAN) {
-            ensure(ctx->dbx, (R ? R : 1) * 4);      // prefix count of core points, per point slot
-            ensure(ctx->dbi, (R ? R : 1));          // noise flag, per point slot
-            CU(launch_detect_dbscan(st, part, offsets, sbase, B, S, csr_v, csr_t, csr_p, (uint32_t *)ctx->dbx.p,
+            ensure(ctx->dbx, cap_rows * 4);         // prefix count of core points, per point slot
+            ensure(ctx->dbi, cap_rows);             // noise flag, per point slot
+            CU(launch_detect_dbscan(st, entries, offsets, sbase, Bl, S, csr_v, csr_t, csr_p, (uint32_t *)ctx->dbx.p,
                                     (uint8_t *)ctx->dbi.p, oc, (uint32_t)out_cap, d_stats, emit_all));
             launches += S ? 1 : 0;
         } else {
@@ -436,7 +512,7 @@ void run_job(tad_ctx *ctx, tad_job *job)
         tad_status &s = job->st;
         s.rows_in = R;
         s.rows_kept = kept;
-        s.rows_owned = kept;
+        s.rows_owned = owned;
         s.points = points;
         s.series = S;
         s.result_rows = out_rows;
@@ -539,6 +615,7 @@ int tad_init(const tad_config *cfg, tad_ctx **out)
 {
     if (!cfg || !out) return TAD_ERR_INVALID_ARG;
     if (cfg->world_size < 1 || cfg->rank < 0 || cfg->rank >= cfg->world_size) return TAD_ERR_INVALID_ARG;
+    if (cfg->world_size > kMaxSeg || (cfg->world_size & (cfg->world_size - 1))) return TAD_ERR_INVALID_ARG;   // 1, 2, 4, 8
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         cudaGetLastError();
@@ -555,6 +632,7 @@ int tad_init(const tad_config *cfg, tad_ctx **out)
     bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
     for (int i = 0; ok && i < kMaxEvents; i++) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
     ok = ok && cudaHostAlloc((void **)&ctx->h_stats, 64 * sizeof(uint32_t), cudaHostAllocDefault) == cudaSuccess;
+    ok = ok && cudaHostAlloc((void **)&ctx->h_small, 64 * sizeof(unsigned long long), cudaHostAllocDefault) == cudaSuccess;
     if (!ok) {
         delete ctx;
         return TAD_ERR_CUDA;
@@ -584,13 +662,15 @@ void tad_shutdown(tad_ctx *ctx)
     nccl_comm_destroy(&ctx->nccl);
     DevBuf *bufs[] = {&ctx->hist, &ctx->offsets, &ctx->cursor, &ctx->big_list, &ctx->big_base, &ctx->csr_p, &ctx->stats, &ctx->part, &ctx->csr_v,
                       &ctx->csr_t, &ctx->nsb, &ctx->npb, &ctx->sbase, &ctx->outb, &ctx->ns_ignore, &ctx->spill, &ctx->dbx,
-                      &ctx->dbi, &ctx->exch, &ctx->scan_sync};
+                      &ctx->dbi, &ctx->exch, &ctx->scan_sync, &ctx->small, &ctx->hist_all, &ctx->seg_off, &ctx->seg_total,
+                      &ctx->entries};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     for (int i = 0; i < 10; i++)
         if (ctx->d_col[i].p) cudaFree(ctx->d_col[i].p);
     for (auto &b : ctx->pinned_pool) cudaFreeHost(b.p);
     if (ctx->h_stats) cudaFreeHost(ctx->h_stats);
+    if (ctx->h_small) cudaFreeHost(ctx->h_small);
     for (int i = 0; i < kMaxEvents; i++)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);

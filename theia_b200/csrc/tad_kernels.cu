@@ -417,8 +417,8 @@ __device__ __forceinline__ uint32_t count_lt_u64(const unsigned long long *a, ui
 }
 
 template <int CAP, int NT, bool VRANK>
-__global__ void __launch_bounds__(NT) group_kernel(Row32 *__restrict__ part, const uint32_t *__restrict__ offsets,
-                                                   uint32_t lo_rows, int sshift,
+__global__ void __launch_bounds__(NT) group_kernel(const SegDesc seg, SeriesEntry *__restrict__ entries,
+                                                   const uint32_t *__restrict__ offsets, uint32_t lo_rows, int sshift,
                                                    uint64_t *__restrict__ csr_v, uint32_t *__restrict__ csr_t,
                                                    uint32_t *__restrict__ csr_p, uint32_t *__restrict__ nsb,
                                                    uint32_t *__restrict__ npb, int reducer)
@@ -446,8 +446,14 @@ __global__ void __launch_bounds__(NT) group_kernel(Row32 *__restrict__ part, con
     if (tid == 0) {
         const uint32_t bytes = n * 32u;
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     :: "r"(smem_u32(s.x)), "l"(part + off_b), "r"(bytes), "r"(bar) : "memory");
+        uint32_t filled = 0;
+        for (int r = 0; r < seg.nseg; r++) {          // one bulk copy per source segment
+            const uint32_t so = seg.off[r][bkt], sc = seg.off[r][bkt + 1] - so;
+            if (sc == 0) continue;
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         :: "r"(smem_u32(s.x) + filled * 32u), "l"(seg.base[r] + so), "r"(sc * 32u), "r"(bar) : "memory");
+            filled += sc;
+        }
     }
 #pragma unroll
     for (int i = 0; i < SPT; i++) s.ht[tid + i * NT] = 0u;
@@ -506,7 +512,7 @@ __global__ void __launch_bounds__(NT) group_kernel(Row32 *__restrict__ part, con
             sum += (w >> 16) | ((w & 0xffffu) ? 0x10000u : 0u);     // low16: points, high16: series
         }
         const uint32_t pre = block_exclusive_scan<NT>(sum, s.warp_sums, &s.total);
-        SeriesEntry *ent = reinterpret_cast<SeriesEntry *>(part + off_b);
+        SeriesEntry *ent = entries + off_b;
 #pragma unroll
         for (int i = 0; i < SPT; i++) {
             const uint32_t w = s.ht[base + i];
@@ -527,38 +533,91 @@ __global__ void __launch_bounds__(NT) group_kernel(Row32 *__restrict__ part, con
     __syncthreads();                       // rows in s.x are dead from here on
     const uint32_t ns = s.total >> 16;
 
-    uint32_t *ts = reinterpret_cast<uint32_t *>(s.x);
-    uint32_t *tout = ts + CAP;
+    uint32_t *ts = reinterpret_cast<uint32_t *>(s.x);                  // times in bin order (scratch)
+    uint32_t *tout = ts + CAP;                                          // times, final order
     unsigned long long *vout = reinterpret_cast<unsigned long long *>(s.x + 8 * CAP);
     uint16_t *pslot = reinterpret_cast<uint16_t *>(s.x + 16 * CAP);   // VRANK: slot of the series at each position
     uint16_t *pout = reinterpret_cast<uint16_t *>(s.x + 18 * CAP);    // VRANK: value rank -> time index
+    uint32_t *binc = reinterpret_cast<uint32_t *>(s.x + 20 * CAP);    // per-bin counts -> exclusive offsets
+    uint32_t *tmin = reinterpret_cast<uint32_t *>(s.x + 24 * CAP);    // per series index
+    uint32_t *tmax = reinterpret_cast<uint32_t *>(s.x + 28 * CAP);
 
+    // ---- R: time-sort every series with an O(n) bucket sort ----------------------------------
+    // A series of cnt points gets cnt bins over [tmin, tmax] (bin = trunc((t - tmin) * cnt / range),
+    // monotone in t), bins are laid out series after series, so ONE block scan of the bin counts
+    // yields every bin's final offset; rows of one bin (1-2 on average) are ordered by counting.
+    for (uint32_t i = tid; i < n; i += NT) { binc[i] = 0u; tmin[i] = 0xffffffffu; tmax[i] = 0u; }
+    __syncthreads();
 #pragma unroll
     for (int j = 0; j < RPT; j++) {
         const uint32_t r = tid + j * NT;
         if (r < n) {
-            const uint32_t slot = mySP[j] & 0xffffu, pos = mySP[j] >> 16;
-            ts[s.soff[slot] + pos] = myT[j];
+            const uint32_t k = s.ht[mySP[j] & 0xffffu] & 0xffffu;
+            atomicMin(&tmin[k], myT[j]);
+            atomicMax(&tmax[k], myT[j]);
         }
     }
     __syncthreads();
-
-    // ---- R: rank every row inside its series by (time, arrival) and place it ------------
+    uint32_t myB[RPT];
+#pragma unroll
+    for (int j = 0; j < RPT; j++) {
+        const uint32_t r = tid + j * NT;
+        myB[j] = 0;
+        if (r < n) {
+            const uint32_t slot = mySP[j] & 0xffffu;
+            const uint32_t w = s.ht[slot], so = s.soff[slot];
+            const uint32_t cnt = w >> 16, k = w & 0xffffu;
+            const uint32_t lo = tmin[k], range = tmax[k] - lo;
+            uint32_t bin = 0;
+            if (range) {
+                const float scale = __uint2float_rn(cnt) / __uint2float_rn(range);
+                bin = min(cnt - 1u, __float2uint_rz(__uint2float_rn(myT[j] - lo) * scale));
+            }
+            const uint32_t ord = atomicAdd(&binc[so + bin], 1u);
+            myB[j] = (so + bin) | (ord << 16);
+        }
+    }
+    __syncthreads();
+    {   // exclusive scan of binc[0, n) in place
+        uint32_t loc[RPT], sum = 0;
+#pragma unroll
+        for (int i = 0; i < RPT; i++) {
+            const uint32_t q = tid * RPT + i;
+            loc[i] = sum;
+            sum += q < n ? binc[q] : 0u;
+        }
+        const uint32_t pre = block_exclusive_scan<NT>(sum, s.warp_sums, &s.total);
+#pragma unroll
+        for (int i = 0; i < RPT; i++) {
+            const uint32_t q = tid * RPT + i;
+            if (q < n) binc[q] = pre + loc[i];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < RPT; j++) {
+        const uint32_t r = tid + j * NT;
+        if (r < n) ts[binc[myB[j] & 0xffffu] + (myB[j] >> 16)] = myT[j];
+    }
+    __syncthreads();
     uint32_t anydup = 0;
 #pragma unroll
     for (int j = 0; j < RPT; j++) {
         const uint32_t r = tid + j * NT;
         if (r < n) {
-            const uint32_t slot = mySP[j] & 0xffffu, pos = mySP[j] >> 16;
-            const uint32_t so = s.soff[slot], cnt = s.ht[slot] >> 16;
+            const uint32_t slot = mySP[j] & 0xffffu;
+            const uint32_t bi = myB[j] & 0xffffu, ord = myB[j] >> 16;
+            const uint32_t b0 = binc[bi], b1 = bi + 1 < n ? binc[bi + 1] : n;
             const uint32_t t = myT[j];
-            // rank = #{q < pos : t_q <= t} + #{q > pos : t_q < t}   (stable by arrival order)
-            uint32_t rank = (t == 0xffffffffu) ? pos : count_lt_u32(ts, so, so + pos, t + 1u);
-            rank += count_lt_u32(ts, so + pos, so + cnt, t);
-            tout[so + rank] = t;
-            vout[so + rank] = myV[j];
-            if (VRANK) pslot[so + rank] = (uint16_t)slot;
-            mySP[j] = (so + rank) | ((rank ? 1u : 0u) << 31);
+            uint32_t pos = b0;
+            for (uint32_t q = b0; q < b1; q++) {
+                const uint32_t tq = ts[q];
+                pos += (tq < t || (tq == t && q - b0 < ord)) ? 1u : 0u;
+            }
+            tout[pos] = t;
+            vout[pos] = myV[j];
+            if (VRANK) pslot[pos] = (uint16_t)slot;
+            mySP[j] = pos | ((pos > s.soff[slot] ? 1u : 0u) << 31);
         }
     }
     __syncthreads();
@@ -573,7 +632,7 @@ __global__ void __launch_bounds__(NT) group_kernel(Row32 *__restrict__ part, con
     uint32_t points = n;
     if (__syncthreads_or((int)anydup)) {
         // ---- D: rare -- reduce duplicates of (key, flowEndSeconds), one thread per slot ----
-        SeriesEntry *ent = reinterpret_cast<SeriesEntry *>(part + off_b);
+        SeriesEntry *ent = entries + off_b;
         uint32_t removed = 0;
         for (int i = 0; i < SPT; i++) {
             const uint32_t sl = tid * SPT + i;
@@ -693,7 +752,7 @@ __device__ __forceinline__ double series_stddev(const uint64_t *__restrict__ v, 
 }
 
 template <int NT>
-__global__ void __launch_bounds__(NT) detect_ewma_kernel(const Row32 *__restrict__ part, const uint32_t *__restrict__ offsets,
+__global__ void __launch_bounds__(NT) detect_ewma_kernel(const SeriesEntry *__restrict__ entries, const uint32_t *__restrict__ offsets,
                                                          const uint32_t *__restrict__ sbase, uint32_t B, uint32_t S,
                                                          const uint64_t *__restrict__ csr_v, const uint32_t *__restrict__ csr_t,
                                                          OutCols out, uint32_t out_cap, uint32_t *__restrict__ stats, int emit_all)
@@ -709,7 +768,7 @@ __global__ void __launch_bounds__(NT) detect_ewma_kernel(const Row32 *__restrict
     uint32_t count = 0;
     if (i < S) {
         const uint32_t b = find_bucket(sbase, B, i);
-        const uint4 *p = reinterpret_cast<const uint4 *>(part + offsets[b] + (i - sbase[b]));
+        const uint4 *p = reinterpret_cast<const uint4 *>(entries + offsets[b] + (i - sbase[b]));
         const uint4 k = p[0], w = p[1];
         e.a = pack64(k.x, k.y); e.b = pack64(k.z, k.w); e.proto = w.x; e.n = w.y; e.off = w.z;
         v = csr_v + e.off;
@@ -759,7 +818,7 @@ __device__ __forceinline__ double sk_brute_d2(double xi, double xj)
 __device__ __forceinline__ bool within_eps(double a, double b) { return fabs(__dsub_rn(a, b)) <= TAD_DBSCAN_EPS; }
 
 template <int NT>
-__global__ void __launch_bounds__(NT) detect_dbscan_kernel(const Row32 *__restrict__ part, const uint32_t *__restrict__ offsets,
+__global__ void __launch_bounds__(NT) detect_dbscan_kernel(const SeriesEntry *__restrict__ entries, const uint32_t *__restrict__ offsets,
                                                            const uint32_t *__restrict__ sbase, uint32_t B, uint32_t S,
                                                            const uint64_t *__restrict__ csr_v, const uint32_t *__restrict__ csr_t,
                                                            uint32_t *__restrict__ csr_p, uint32_t *__restrict__ scratch_pc,
@@ -778,7 +837,7 @@ __global__ void __launch_bounds__(NT) detect_dbscan_kernel(const Row32 *__restri
     uint32_t count = 0;
     if (i < S) {
         const uint32_t b = find_bucket(sbase, B, i);
-        const uint4 *p = reinterpret_cast<const uint4 *>(part + offsets[b] + (i - sbase[b]));
+        const uint4 *p = reinterpret_cast<const uint4 *>(entries + offsets[b] + (i - sbase[b]));
         const uint4 k = p[0], w = p[1];
         e.a = pack64(k.x, k.y); e.b = pack64(k.z, k.w); e.proto = w.x; e.n = w.y; e.off = w.z; e.pad = w.w;
         v = csr_v + e.off;
@@ -926,7 +985,8 @@ cudaError_t launch_bucket_scan(cudaStream_t st, const uint32_t *hist, uint32_t *
 }
 
 template <int CAP, bool VRANK>
-static cudaError_t launch_group_class(cudaStream_t st, Row32 *part, const uint32_t *offsets, uint32_t B, uint32_t lo_rows,
+static cudaError_t launch_group_class(cudaStream_t st, const SegDesc &seg, SeriesEntry *entries, const uint32_t *offsets,
+                                      uint32_t B, uint32_t lo_rows,
                                       int sshift, uint64_t *csr_v, uint32_t *csr_t, uint32_t *csr_p, uint32_t *nsb,
                                       uint32_t *npb, int reducer)
 {
@@ -938,27 +998,28 @@ static cudaError_t launch_group_class(cudaStream_t st, Row32 *part, const uint32
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    kern<<<B, kGroupThreads, sizeof(S), st>>>(part, offsets, lo_rows, sshift, csr_v, csr_t, csr_p, nsb, npb, reducer);
+    kern<<<B, kGroupThreads, sizeof(S), st>>>(seg, entries, offsets, lo_rows, sshift, csr_v, csr_t, csr_p, nsb, npb, reducer);
     return cudaGetLastError();
 }
 
 // Two shared-memory capacity classes: most buckets hold <= kGroupCapSmall rows and run at a higher
 // occupancy; the rest (up to kGroupCap rows) use the big configuration.  Empty buckets keep the
 // zeroes the caller memset into nsb / npb.
-cudaError_t launch_group(cudaStream_t st, Row32 *part, const uint32_t *offsets, uint32_t B, int logB, uint64_t *csr_v,
-                         uint32_t *csr_t, uint32_t *csr_p, uint32_t *nsb, uint32_t *npb, int reducer)
+cudaError_t launch_group(cudaStream_t st, const SegDesc &seg, SeriesEntry *entries, const uint32_t *offsets, uint32_t B,
+                         int logB, uint64_t *csr_v, uint32_t *csr_t, uint32_t *csr_p, uint32_t *nsb, uint32_t *npb,
+                         int reducer)
 {
     int sshift = 64 - logB - 12;          // 12 hash bits below the bucket bits pick the slot
     if (sshift < 0) sshift = 0;
     cudaError_t e;
     if (csr_p) {
-        e = launch_group_class<kGroupCapSmall, true>(st, part, offsets, B, 0, sshift, csr_v, csr_t, csr_p, nsb, npb, reducer);
+        e = launch_group_class<kGroupCapSmall, true>(st, seg, entries, offsets, B, 0, sshift, csr_v, csr_t, csr_p, nsb, npb, reducer);
         if (e == cudaSuccess)
-            e = launch_group_class<kGroupCap, true>(st, part, offsets, B, kGroupCapSmall, sshift, csr_v, csr_t, csr_p, nsb, npb, reducer);
+            e = launch_group_class<kGroupCap, true>(st, seg, entries, offsets, B, kGroupCapSmall, sshift, csr_v, csr_t, csr_p, nsb, npb, reducer);
     } else {
-        e = launch_group_class<kGroupCapSmall, false>(st, part, offsets, B, 0, sshift, csr_v, csr_t, csr_p, nsb, npb, reducer);
+        e = launch_group_class<kGroupCapSmall, false>(st, seg, entries, offsets, B, 0, sshift, csr_v, csr_t, csr_p, nsb, npb, reducer);
         if (e == cudaSuccess)
-            e = launch_group_class<kGroupCap, false>(st, part, offsets, B, kGroupCapSmall, sshift, csr_v, csr_t, csr_p, nsb, npb, reducer);
+            e = launch_group_class<kGroupCap, false>(st, seg, entries, offsets, B, kGroupCapSmall, sshift, csr_v, csr_t, csr_p, nsb, npb, reducer);
     }
     return e;
 }
@@ -970,27 +1031,67 @@ cudaError_t launch_series_scan(cudaStream_t st, const uint32_t *nsb, const uint3
     return cudaGetLastError();
 }
 
-cudaError_t launch_detect_ewma(cudaStream_t st, const Row32 *part, const uint32_t *offsets, const uint32_t *sbase, uint32_t B,
+cudaError_t launch_detect_ewma(cudaStream_t st, const SeriesEntry *entries, const uint32_t *offsets, const uint32_t *sbase, uint32_t B,
                                uint32_t S, const uint64_t *csr_v, const uint32_t *csr_t, const OutCols &out,
                                uint32_t out_cap, uint32_t *stats, int emit_all)
 {
     if (S == 0) return cudaSuccess;
     constexpr int NT = 128;
-    detect_ewma_kernel<NT><<<(S + NT - 1) / NT, NT, 0, st>>>(part, offsets, sbase, B, S, csr_v, csr_t, out, out_cap, stats,
+    detect_ewma_kernel<NT><<<(S + NT - 1) / NT, NT, 0, st>>>(entries, offsets, sbase, B, S, csr_v, csr_t, out, out_cap, stats,
                                                             emit_all);
     return cudaGetLastError();
 }
 
-cudaError_t launch_detect_dbscan(cudaStream_t st, const Row32 *part, const uint32_t *offsets, const uint32_t *sbase,
+cudaError_t launch_detect_dbscan(cudaStream_t st, const SeriesEntry *entries, const uint32_t *offsets, const uint32_t *sbase,
                                  uint32_t B, uint32_t S, const uint64_t *csr_v, const uint32_t *csr_t, const uint32_t *csr_p,
                                  uint32_t *scratch_pc, uint8_t *scratch_flag, const OutCols &out, uint32_t out_cap,
                                  uint32_t *stats, int emit_all)
 {
     if (S == 0) return cudaSuccess;
     constexpr int NT = 128;
-    detect_dbscan_kernel<NT><<<(S + NT - 1) / NT, NT, 0, st>>>(part, offsets, sbase, B, S, csr_v, csr_t,
+    detect_dbscan_kernel<NT><<<(S + NT - 1) / NT, NT, 0, st>>>(entries, offsets, sbase, B, S, csr_v, csr_t,
                                                               const_cast<uint32_t *>(csr_p), scratch_pc, scratch_flag, out,
                                                               out_cap, stats, emit_all);
+    return cudaGetLastError();
+}
+
+// ----------------------------------------------------------------------------------------
+// multi-GPU: segment offsets of this rank's bucket range from the all-gathered histograms
+// ----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) segment_scan_kernel(const uint32_t *__restrict__ hist_all, uint32_t B_global, uint32_t b_lo,
+                                                            uint32_t B_local, uint32_t *__restrict__ seg_off,
+                                                            unsigned long long *__restrict__ seg_rows)
+{
+    __shared__ uint32_t total_s;
+    const uint32_t r = blockIdx.x;
+    const uint32_t *h = hist_all + (size_t)r * B_global + b_lo;
+    uint32_t *out = seg_off + (size_t)r * (B_local + 1);
+    const uint32_t per = (B_local + 1023) / 1024;
+    const uint32_t lo = min(B_local, threadIdx.x * per), hi = min(B_local, lo + per);
+    uint32_t sum = 0;
+    for (uint32_t i = lo; i < hi; i++) sum += h[i];
+    const uint32_t pre = block_exclusive_scan_1024(sum, &total_s);
+    uint32_t run = pre;
+    for (uint32_t i = lo; i < hi; i++) { out[i] = run; run += h[i]; }
+    if (threadIdx.x == 0) { out[B_local] = total_s; seg_rows[r] = total_s; }
+}
+
+__global__ void __launch_bounds__(256) segment_total_kernel(const uint32_t *__restrict__ hist_all, uint32_t B_global, uint32_t b_lo,
+                                                            uint32_t B_local, int nseg, uint32_t *__restrict__ total)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < B_local; i += gridDim.x * blockDim.x) {
+        uint32_t t = 0;
+        for (int r = 0; r < nseg; r++) t += hist_all[(size_t)r * B_global + b_lo + i];
+        total[i] = t;
+    }
+}
+
+cudaError_t launch_segment_scan(cudaStream_t st, const uint32_t *hist_all, uint32_t B_global, uint32_t b_lo, uint32_t B_local,
+                                int nseg, uint32_t *seg_off, uint32_t *total, unsigned long long *seg_rows)
+{
+    segment_scan_kernel<<<nseg, 1024, 0, st>>>(hist_all, B_global, b_lo, B_local, seg_off, seg_rows);
+    const uint32_t grid = (B_local + 255) / 256;
+    segment_total_kernel<<<grid > 1184 ? 1184 : grid, 256, 0, st>>>(hist_all, B_global, b_lo, B_local, nseg, total);
     return cudaGetLastError();
 }
 

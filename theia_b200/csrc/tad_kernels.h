@@ -13,14 +13,17 @@ cudaError_t launch_bucket_scan(cudaStream_t st, const uint32_t *hist, uint32_t *
 size_t scan_sync_bytes();   // zero-initialised once; epoch must be > 0 and differ between launches
 // csr_p != nullptr: also rank every series by value and write the permutation (value rank -> time
 // index) the DBSCAN detector sweeps over.
-cudaError_t launch_group(cudaStream_t st, Row32 *part, const uint32_t *offsets, uint32_t B, int logB, uint64_t *csr_v,
-                         uint32_t *csr_t, uint32_t *csr_p, uint32_t *nsb, uint32_t *npb, int reducer);
+// `offsets` are the (virtual, contiguous) bucket offsets used for entries / csr arrays; the rows
+// themselves are read through `seg`.
+cudaError_t launch_group(cudaStream_t st, const SegDesc &seg, SeriesEntry *entries, const uint32_t *offsets, uint32_t B,
+                         int logB, uint64_t *csr_v, uint32_t *csr_t, uint32_t *csr_p, uint32_t *nsb, uint32_t *npb,
+                         int reducer);
 cudaError_t launch_series_scan(cudaStream_t st, const uint32_t *nsb, const uint32_t *npb, uint32_t *sbase, uint32_t B,
                                uint32_t *stats, void *scan_sync, uint32_t epoch);
-cudaError_t launch_detect_ewma(cudaStream_t st, const Row32 *part, const uint32_t *offsets, const uint32_t *sbase, uint32_t B,
+cudaError_t launch_detect_ewma(cudaStream_t st, const SeriesEntry *entries, const uint32_t *offsets, const uint32_t *sbase, uint32_t B,
                                uint32_t S, const uint64_t *csr_v, const uint32_t *csr_t, const OutCols &out,
                                uint32_t out_cap, uint32_t *stats, int emit_all);
-cudaError_t launch_detect_dbscan(cudaStream_t st, const Row32 *part, const uint32_t *offsets, const uint32_t *sbase,
+cudaError_t launch_detect_dbscan(cudaStream_t st, const SeriesEntry *entries, const uint32_t *offsets, const uint32_t *sbase,
                                  uint32_t B, uint32_t S, const uint64_t *csr_v, const uint32_t *csr_t, const uint32_t *csr_p,
                                  uint32_t *scratch_pc, uint8_t *scratch_flag, const OutCols &out, uint32_t out_cap,
                                  uint32_t *stats, int emit_all);
@@ -30,8 +33,16 @@ cudaError_t launch_detect_dbscan(cudaStream_t st, const Row32 *part, const uint3
 // same per-series arrays / in-place series entries / nsb / npb the group kernel produces.
 // `scratch` must hold spill_scratch_bytes(big_rows) bytes.  Returns launches through *launches.
 size_t spill_scratch_bytes(uint64_t big_rows);
-cudaError_t run_spill(cudaStream_t st, Row32 *part, const uint32_t *offsets, const uint32_t *big_list,
+cudaError_t run_spill(cudaStream_t st, const SegDesc &seg, SeriesEntry *entries, const uint32_t *offsets, const uint32_t *big_list,
                       const uint32_t *big_base, uint32_t n_big, uint64_t big_rows, void *scratch, size_t scratch_bytes,
                       uint64_t *csr_v, uint32_t *csr_t, uint32_t *nsb, uint32_t *npb, int reducer, int *launches);
 
 }  // namespace tad
+
+namespace tad {
+// Multi-GPU: per-source segment offsets and total bucket sizes of this rank's bucket range from the
+// all-gathered histograms.  hist_all[r * B_global + b]; range = [b_lo, b_lo + B_local).
+cudaError_t launch_segment_scan(cudaStream_t st, const uint32_t *hist_all, uint32_t B_global, uint32_t b_lo, uint32_t B_local,
+                                int nseg, uint32_t *seg_off /* nseg x (B_local+1) */, uint32_t *total /* B_local */,
+                                unsigned long long *seg_rows /* nseg */);
+}

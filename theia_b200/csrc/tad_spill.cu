@@ -26,19 +26,23 @@ struct SpillDecomposer {
     }
 };
 
-__global__ void __launch_bounds__(256) spill_gather_kernel(const Row32 *__restrict__ part, const uint32_t *__restrict__ offsets,
-                                                           const uint32_t *__restrict__ big_list,
+__global__ void __launch_bounds__(256) spill_gather_kernel(const SegDesc seg, const uint32_t *__restrict__ big_list,
                                                            const uint32_t *__restrict__ big_base, SpillRow *__restrict__ in)
 {
     const uint32_t j = blockIdx.x;
     const uint32_t b = big_list[j];
-    const uint32_t off = offsets[b], n = offsets[b + 1] - off, base = big_base[j];
-    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-        const Row32 r = part[off + i];
-        SpillRow s;
-        s.h = key_hash(r.a, r.b, r.proto);
-        s.a = r.a; s.b = r.b; s.value = r.value; s.proto = r.proto; s.t = r.t;
-        in[base + i] = s;
+    uint32_t base = big_base[j];
+    for (int sg = 0; sg < seg.nseg; sg++) {
+        const uint32_t off = seg.off[sg][b], n = seg.off[sg][b + 1] - off;
+        const Row32 *rows = seg.base[sg] + off;
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+            const Row32 r = rows[i];
+            SpillRow s;
+            s.h = key_hash(r.a, r.b, r.proto);
+            s.a = r.a; s.b = r.b; s.value = r.value; s.proto = r.proto; s.t = r.t;
+            in[base + i] = s;
+        }
+        base += n;
     }
 }
 
@@ -74,7 +78,7 @@ __global__ void __launch_bounds__(256) spill_place_kernel(const SpillRow *__rest
                                                           uint32_t M, const uint32_t *__restrict__ offsets,
                                                           const uint32_t *__restrict__ big_list,
                                                           const uint32_t *__restrict__ big_base, uint32_t n_big,
-                                                          Row32 *__restrict__ part, uint64_t *__restrict__ csr_v,
+                                                          SeriesEntry *__restrict__ entries, uint64_t *__restrict__ csr_v,
                                                           uint32_t *__restrict__ csr_t, uint32_t *__restrict__ nsb,
                                                           uint32_t *__restrict__ npb, int reducer)
 {
@@ -90,7 +94,7 @@ __global__ void __launch_bounds__(256) spill_place_kernel(const SpillRow *__rest
     const uint32_t off_b = offsets[b];
     const uint32_t k = (uint32_t)(sc >> 32) - (uint32_t)(bsc >> 32) - 1u;       // series index inside the bucket
     const uint32_t p = (uint32_t)sc - (uint32_t)bsc - 1u;                        // point index inside the bucket
-    SeriesEntry *ent = reinterpret_cast<SeriesEntry *>(part + off_b);
+    SeriesEntry *ent = entries + off_b;
     if (PASS == 0) {
         if (key_head) {
             const SpillRow r = rows[i];
@@ -134,7 +138,7 @@ size_t spill_scratch_bytes(uint64_t M)
     return 2 * align256(M * sizeof(SpillRow)) + 2 * align256(M * 8) + align256(cub_temp_bytes(M)) + 1024;
 }
 
-cudaError_t run_spill(cudaStream_t st, Row32 *part, const uint32_t *offsets, const uint32_t *big_list,
+cudaError_t run_spill(cudaStream_t st, const SegDesc &seg, SeriesEntry *entries, const uint32_t *offsets, const uint32_t *big_list,
                       const uint32_t *big_base, uint32_t n_big, uint64_t big_rows, void *scratch, size_t scratch_bytes,
                       uint64_t *csr_v, uint32_t *csr_t, uint32_t *nsb, uint32_t *npb, int reducer, int *launches)
 {
@@ -154,7 +158,7 @@ cudaError_t run_spill(cudaStream_t st, Row32 *part, const uint32_t *offsets, con
     void *temp = base;
     size_t temp_bytes = cub_temp_bytes(M);
 
-    spill_gather_kernel<<<n_big, 256, 0, st>>>(part, offsets, big_list, big_base, in);
+    spill_gather_kernel<<<n_big, 256, 0, st>>>(seg, big_list, big_base, in);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     size_t tb = temp_bytes;
@@ -165,9 +169,9 @@ cudaError_t run_spill(cudaStream_t st, Row32 *part, const uint32_t *offsets, con
     tb = temp_bytes;
     e = cub::DeviceScan::InclusiveSum(temp, tb, (const uint64_t *)flags, scan, M, st);
     if (e != cudaSuccess) return e;
-    spill_place_kernel<0><<<grid, 256, 0, st>>>(out, scan, M, offsets, big_list, big_base, n_big, part, csr_v, csr_t, nsb, npb,
+    spill_place_kernel<0><<<grid, 256, 0, st>>>(out, scan, M, offsets, big_list, big_base, n_big, entries, csr_v, csr_t, nsb, npb,
                                                reducer);
-    spill_place_kernel<1><<<grid, 256, 0, st>>>(out, scan, M, offsets, big_list, big_base, n_big, part, csr_v, csr_t, nsb, npb,
+    spill_place_kernel<1><<<grid, 256, 0, st>>>(out, scan, M, offsets, big_list, big_base, n_big, entries, csr_v, csr_t, nsb, npb,
                                                reducer);
     *launches = 4 + 8;        // ours + CUB's sort/scan passes (approximate)
     return cudaGetLastError();
