@@ -176,7 +176,10 @@ def run_ours(args):
     if dist is not None:
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
     ms_dev, ms_wall = float(stats[0]), float(stats[1])
-    total_rows = rows * world
+    tr = torch.tensor([rows], device=dev, dtype=torch.int64)
+    if dist is not None:
+        dist.all_reduce(tr)
+    total_rows = int(tr[0])
 
     # ---- e2e: host (pinned) buffers through the C ABI, H2D + D2H inside the timed region --------
     if args.no_e2e:

@@ -138,3 +138,47 @@ def make_flows_torch(n_series: int, points_per_series: int, seed: int, device):
         "value": val,
     }
     return cols
+
+
+def make_flows_torch_sharded(series_per_gpu: int, points_per_series: int, seed: int, device, rank: int, world: int):
+    """Rank `rank`'s shard of a table with world * series_per_gpu connections: every connection's points
+    are dealt round-robin over the ranks (point k lives on rank k % world), so each rank holds
+    series_per_gpu * points rows and NO connection is local before the exchange."""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)                      # same key attributes on every rank
+    S, n = series_per_gpu * world, points_per_series
+
+    def ri(gen, lo, hi, size):
+        return torch.randint(lo, hi, (size,), generator=gen, device=device, dtype=torch.int64)
+
+    src_ip = (10 << 24) + ri(g, 0, 1 << 24, S)
+    dst_ip = (10 << 24) + ri(g, 0, 1 << 24, S)
+    src_port = ri(g, 1024, 65536, S)
+    ports = torch.as_tensor(SERVICE_PORTS.astype(np.int64), device=device)
+    dst_port = ports[ri(g, 0, len(SERVICE_PORTS), S)]
+    proto = torch.where(torch.rand(S, generator=g, device=device) < 0.8, 6, 17)
+    flow_start = T0 + ri(g, 0, 3600, S)
+    base = torch.exp(torch.empty(S, device=device, dtype=torch.float64).uniform_(
+        float(np.log(1e6)), float(np.log(1e10)), generator=g))
+    g2 = torch.Generator(device=device)
+    g2.manual_seed(seed * 1000 + 17 + rank)   # per-rank noise and shuffle
+    npl = (n - rank + world - 1) // world     # points k = rank+1, rank+1+world, ... <= n
+    R = S * npl
+    perm = torch.randperm(R, generator=g2, device=device)
+    sid = perm // npl
+    k = (perm % npl) * world + rank + 1       # 1..n, the points this rank holds
+    b = base[sid]
+    val = b + torch.randn(R, generator=g2, device=device, dtype=torch.float64) * (1e-3 * b)
+    spike = torch.rand(R, generator=g2, device=device) < 0.01
+    fac = torch.as_tensor(SPIKE_FACTORS, device=device)[ri(g2, 0, 3, R)]
+    val = torch.where(spike, val * fac, val)
+    val = torch.clamp(torch.round(val), min=1.0).to(torch.int64)
+    del b, spike, fac, perm
+    return {
+        "src_ip": src_ip[sid].to(torch.int32), "src_port": src_port[sid].to(torch.int16),
+        "dst_ip": dst_ip[sid].to(torch.int32), "dst_port": dst_port[sid].to(torch.int16),
+        "proto": proto[sid].to(torch.uint8), "flow_start": flow_start[sid].to(torch.int32),
+        "flow_end": (flow_start[sid] + 60 * k).to(torch.int32),
+        "value": val,
+    }
