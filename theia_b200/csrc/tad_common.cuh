@@ -88,8 +88,10 @@ enum {
     ST_COUNT
 };
 
-constexpr int kGroupCap = 2048;       // rows a bucket may hold to take the shared-memory path
-constexpr int kGroupCapSmall = 1024;  // first capacity class (higher occupancy)
+constexpr int kGroupCap = 4096;       // rows a bucket may hold to take the shared-memory path (largest class)
+constexpr int kGroupCapMid = 2048;    // second capacity class
+constexpr int kGroupCapSmall = 1024;  // first capacity class (highest occupancy)
+constexpr int kGroupTarget = 768;     // mean rows per bucket pick_logb aims for
 constexpr int kGroupThreads = 256;
 constexpr int kGroupHT = 2 * kGroupCap;
 

@@ -32,6 +32,7 @@ struct PinnedBlock {
 };
 
 constexpr int kMaxEvents = 24;
+constexpr int kMaxChunks = 16;          // host-resident input is copied and histogrammed in chunks
 constexpr int kTotalStages = 6;   // ingest, partition, exchange, group, detect, egress
 
 double now_ms()
@@ -58,8 +59,10 @@ struct tad_job {
 
 struct tad_ctx {
     tad_config cfg{};
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
     cudaEvent_t ev[kMaxEvents]{};
+    cudaEvent_t chunk_ev[kMaxChunks]{};
+    cudaEvent_t start_ev = nullptr;
     std::mutex mu;
     std::condition_variable cv;
     std::deque<tad_job *> queue;
@@ -162,7 +165,7 @@ int pick_logb(const tad_ctx *ctx, uint64_t rows)
 {
     if (ctx->debug_logb >= 0) return ctx->debug_logb;
     // mean bucket ~ 0.375 * capacity: connection sizes are lumpy, so leave head-room
-    const uint64_t target = (uint64_t)(kGroupCap * 3 / 8);
+    const uint64_t target = (uint64_t)kGroupTarget;
     int logb = 0;
     while (logb < 22 && (rows >> logb) > target) logb++;
     return logb;
@@ -259,9 +262,11 @@ void run_job(tad_ctx *ctx, tad_job *job)
     }
 
     // ---- ingest: host columns -> device (device-resident columns are used in place) -------
+    // Host input is copied in chunks on a second stream; the bucket histogram is additive, so the
+    // histogram of chunk i runs while chunk i+1 is still on the PCIe bus.
     ColPtrs c{};
     const void *dcol[10];
-    mark(-1);
+    const bool host_input = hc.mem != TAD_MEM_DEVICE && R > 0;
     for (int i = 0; i < 10; i++) {
         void *src = col_ptr(hc, i);
         dcol[i] = nullptr;
@@ -270,11 +275,37 @@ void run_job(tad_ctx *ctx, tad_job *job)
             dcol[i] = src;
         } else {
             ensure(ctx->d_col[i], col_bytes(i, R));
-            CU(cudaMemcpyAsync(ctx->d_col[i].p, src, col_bytes(i, R), cudaMemcpyHostToDevice, st));
             dcol[i] = ctx->d_col[i].p;
         }
     }
-    mark(TAD_PHASE_H2D);
+    int nchunks = 1;
+    if (host_input) {
+        nchunks = (int)((R + (8u << 20) - 1) / (8u << 20));          // ~8M rows (232 MB) per chunk
+        if (nchunks > kMaxChunks) nchunks = kMaxChunks;
+        if (nchunks < 1) nchunks = 1;
+    }
+    auto chunk_lo = [&](int k) { return ((R * (uint64_t)k / nchunks) + 15) & ~uint64_t(15); };   // keeps every column 16-byte aligned
+    auto chunk_range = [&](int k, uint64_t &lo, uint64_t &hi) {
+        lo = k == 0 ? 0 : (chunk_lo(k) < R ? chunk_lo(k) : R);
+        hi = k + 1 == nchunks ? R : (chunk_lo(k + 1) < R ? chunk_lo(k + 1) : R);
+    };
+    mark(-1);
+    if (host_input) {
+        CU(cudaEventRecord(ctx->start_ev, st));
+        CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->start_ev, 0));   // workspace of the previous job is free
+        for (int k = 0; k < nchunks; k++) {
+            uint64_t lo, hi;
+            chunk_range(k, lo, hi);
+            for (int i = 0; i < 10 && hi > lo; i++) {
+                const char *src = static_cast<const char *>(col_ptr(hc, i));
+                if (!src) continue;
+                const size_t w = col_bytes(i, 1);
+                CU(cudaMemcpyAsync(static_cast<char *>(ctx->d_col[i].p) + lo * w, src + lo * w, (hi - lo) * w,
+                                   cudaMemcpyHostToDevice, ctx->copy_stream));
+            }
+            CU(cudaEventRecord(ctx->chunk_ev[k], ctx->copy_stream));
+        }
+    }
     c.src_ip = (const uint32_t *)dcol[0]; c.dst_ip = (const uint32_t *)dcol[1];
     c.src_port = (const uint16_t *)dcol[2]; c.dst_port = (const uint16_t *)dcol[3];
     c.proto = (const uint8_t *)dcol[4]; c.flow_start = (const uint32_t *)dcol[5];
@@ -332,8 +363,30 @@ void run_job(tad_ctx *ctx, tad_job *job)
     CU(cudaMemsetAsync(nsb, 0, (size_t)Bl * 4, st));
     CU(cudaMemsetAsync(npb, 0, (size_t)Bl * 4, st));
     mark(-1);
-    CU(launch_hist(st, c, R, f, logB, hist)); launches += R ? 1 : 0;
-    mark(TAD_PHASE_HIST);
+    if (host_input) {
+        for (int k = 0; k < nchunks; k++) {
+            uint64_t lo, hi;
+            chunk_range(k, lo, hi);
+            CU(cudaStreamWaitEvent(st, ctx->chunk_ev[k], 0));
+            if (hi <= lo) continue;
+            ColPtrs ck = c;
+            if (ck.src_ip) ck.src_ip += lo;
+            if (ck.dst_ip) ck.dst_ip += lo;
+            if (ck.src_port) ck.src_port += lo;
+            if (ck.dst_port) ck.dst_port += lo;
+            if (ck.proto) ck.proto += lo;
+            if (ck.flow_start) ck.flow_start += lo;
+            if (ck.flow_end) ck.flow_end += lo;
+            if (ck.value) ck.value += lo;
+            if (ck.src_ns) ck.src_ns += lo;
+            if (ck.dst_ns) ck.dst_ns += lo;
+            CU(launch_hist(st, ck, hi - lo, f, logB, hist)); launches++;
+        }
+        mark(TAD_PHASE_H2D);          // copy + overlapped histogram of all chunks
+    } else {
+        CU(launch_hist(st, c, R, f, logB, hist)); launches += R ? 1 : 0;
+        mark(TAD_PHASE_HIST);
+    }
     // single GPU: these are the final bucket offsets; multi GPU: offsets inside the local send buffer
     CU(launch_bucket_scan(st, hist, offsets, cursor, B, world > 1 ? 0xffffffffu : (uint32_t)kGroupCap, big_list, big_base,
                           d_stats, ctx->scan_sync.p, ++ctx->scan_epoch)); launches++;
@@ -414,7 +467,12 @@ void run_job(tad_ctx *ctx, tad_job *job)
         csr_p = (uint32_t *)ctx->csr_p.p;
     }
     mark(-1);
-    CU(launch_group(st, seg, entries, offsets, Bl, logB, csr_v, csr_t, csr_p, nsb, npb, sp.reducer)); launches += 2;
+    {
+        int l = 0;
+        CU(launch_group(st, seg, entries, offsets, Bl, logB, ctx->h_stats[ST_MAXBUCKET], csr_v, csr_t, csr_p, nsb, npb,
+                        sp.reducer, &l));
+        launches += l;
+    }
     mark(TAD_PHASE_GROUP);
     if (n_big) {
         const size_t need = spill_scratch_bytes(big_rows);
@@ -503,7 +561,7 @@ void run_job(tad_ctx *ctx, tad_job *job)
     // device span excludes the H2D/D2H copies: first partition event .. last detect event
     int first_k = -1, last_k = -1;
     for (int i = 0; i < nev; i++) {
-        if (ev_phase[i] == TAD_PHASE_HIST && first_k < 0) first_k = i - 1;
+        if ((ev_phase[i] == TAD_PHASE_HIST || ev_phase[i] == TAD_PHASE_H2D) && first_k < 0) first_k = i - 1;
         if (ev_phase[i] == TAD_PHASE_DETECT) last_k = i;
     }
     if (first_k >= 0 && last_k > first_k) CU(cudaEventElapsedTime(&total, ctx->ev[first_k], ctx->ev[last_k]));
@@ -630,6 +688,9 @@ int tad_init(const tad_config *cfg, tad_ctx **out)
     if (const char *e = getenv("TAD_DEBUG_LOGB")) ctx->debug_logb = atoi(e);
     cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, cfg->device);
     bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; ok && i < kMaxChunks; i++) ok = cudaEventCreateWithFlags(&ctx->chunk_ev[i], cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&ctx->start_ev, cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; ok && i < kMaxEvents; i++) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
     ok = ok && cudaHostAlloc((void **)&ctx->h_stats, 64 * sizeof(uint32_t), cudaHostAllocDefault) == cudaSuccess;
     ok = ok && cudaHostAlloc((void **)&ctx->h_small, 64 * sizeof(unsigned long long), cudaHostAllocDefault) == cudaSuccess;
@@ -673,6 +734,10 @@ void tad_shutdown(tad_ctx *ctx)
     if (ctx->h_small) cudaFreeHost(ctx->h_small);
     for (int i = 0; i < kMaxEvents; i++)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    for (int i = 0; i < kMaxChunks; i++)
+        if (ctx->chunk_ev[i]) cudaEventDestroy(ctx->chunk_ev[i]);
+    if (ctx->start_ev) cudaEventDestroy(ctx->start_ev);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

@@ -16,6 +16,7 @@
 #include "tad_kernels.h"
 
 #include <cstdio>
+#include <cstdlib>
 
 namespace tad {
 
@@ -984,44 +985,58 @@ cudaError_t launch_bucket_scan(cudaStream_t st, const uint32_t *hist, uint32_t *
     return cudaGetLastError();
 }
 
-template <int CAP, bool VRANK>
+template <int CAP, int NT, bool VRANK>
 static cudaError_t launch_group_class(cudaStream_t st, const SegDesc &seg, SeriesEntry *entries, const uint32_t *offsets,
                                       uint32_t B, uint32_t lo_rows,
                                       int sshift, uint64_t *csr_v, uint32_t *csr_t, uint32_t *csr_p, uint32_t *nsb,
                                       uint32_t *npb, int reducer)
 {
-    using S = GroupSmem<CAP, kGroupThreads>;
+    using S = GroupSmem<CAP, NT>;
     static bool configured = false;
-    auto kern = group_kernel<CAP, kGroupThreads, VRANK>;
+    auto kern = group_kernel<CAP, NT, VRANK>;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(S));
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    kern<<<B, kGroupThreads, sizeof(S), st>>>(seg, entries, offsets, lo_rows, sshift, csr_v, csr_t, csr_p, nsb, npb, reducer);
+    kern<<<B, NT, sizeof(S), st>>>(seg, entries, offsets, lo_rows, sshift, csr_v, csr_t, csr_p, nsb, npb, reducer);
     return cudaGetLastError();
 }
 
-// Two shared-memory capacity classes: most buckets hold <= kGroupCapSmall rows and run at a higher
-// occupancy; the rest (up to kGroupCap rows) use the big configuration.  Empty buckets keep the
-// zeroes the caller memset into nsb / npb.
-cudaError_t launch_group(cudaStream_t st, const SegDesc &seg, SeriesEntry *entries, const uint32_t *offsets, uint32_t B,
-                         int logB, uint64_t *csr_v, uint32_t *csr_t, uint32_t *csr_p, uint32_t *nsb, uint32_t *npb,
-                         int reducer)
+// Three shared-memory capacity classes (1024 / 2048 / 4096 rows): most buckets fit the first and run at
+// the highest occupancy; `max_bucket` (known on the host after the bucket scan) lets the launcher skip
+// classes no bucket needs.  Empty buckets keep the zeroes the caller memset into nsb / npb.
+template <bool VRANK>
+static cudaError_t launch_group_all(cudaStream_t st, const SegDesc &seg, SeriesEntry *entries, const uint32_t *offsets,
+                                    uint32_t B, int sshift, uint32_t max_bucket, uint64_t *csr_v, uint32_t *csr_t,
+                                    uint32_t *csr_p, uint32_t *nsb, uint32_t *npb, int reducer, int *launches)
 {
-    int sshift = 64 - logB - 12;          // 12 hash bits below the bucket bits pick the slot
-    if (sshift < 0) sshift = 0;
-    cudaError_t e;
-    if (csr_p) {
-        e = launch_group_class<kGroupCapSmall, true>(st, seg, entries, offsets, B, 0, sshift, csr_v, csr_t, csr_p, nsb, npb, reducer);
-        if (e == cudaSuccess)
-            e = launch_group_class<kGroupCap, true>(st, seg, entries, offsets, B, kGroupCapSmall, sshift, csr_v, csr_t, csr_p, nsb, npb, reducer);
-    } else {
-        e = launch_group_class<kGroupCapSmall, false>(st, seg, entries, offsets, B, 0, sshift, csr_v, csr_t, csr_p, nsb, npb, reducer);
-        if (e == cudaSuccess)
-            e = launch_group_class<kGroupCap, false>(st, seg, entries, offsets, B, kGroupCapSmall, sshift, csr_v, csr_t, csr_p, nsb, npb, reducer);
+    cudaError_t e = launch_group_class<kGroupCapSmall, 256, VRANK>(st, seg, entries, offsets, B, 0, sshift, csr_v, csr_t, csr_p,
+                                                                   nsb, npb, reducer);
+    *launches = 1;
+    if (e == cudaSuccess && max_bucket > (uint32_t)kGroupCapSmall) {
+        e = launch_group_class<kGroupCapMid, 256, VRANK>(st, seg, entries, offsets, B, kGroupCapSmall, sshift, csr_v, csr_t,
+                                                         csr_p, nsb, npb, reducer);
+        ++*launches;
+    }
+    if (e == cudaSuccess && max_bucket > (uint32_t)kGroupCapMid) {
+        e = launch_group_class<kGroupCap, 512, VRANK>(st, seg, entries, offsets, B, kGroupCapMid, sshift, csr_v, csr_t, csr_p,
+                                                      nsb, npb, reducer);
+        ++*launches;
     }
     return e;
+}
+
+cudaError_t launch_group(cudaStream_t st, const SegDesc &seg, SeriesEntry *entries, const uint32_t *offsets, uint32_t B,
+                         int logB, uint32_t max_bucket, uint64_t *csr_v, uint32_t *csr_t, uint32_t *csr_p, uint32_t *nsb,
+                         uint32_t *npb, int reducer, int *launches)
+{
+    int sshift = 64 - logB - 13;          // 13 hash bits below the bucket bits pick the slot
+    if (sshift < 0) sshift = 0;
+    return csr_p ? launch_group_all<true>(st, seg, entries, offsets, B, sshift, max_bucket, csr_v, csr_t, csr_p, nsb, npb,
+                                          reducer, launches)
+                 : launch_group_all<false>(st, seg, entries, offsets, B, sshift, max_bucket, csr_v, csr_t, csr_p, nsb, npb,
+                                           reducer, launches);
 }
 
 cudaError_t launch_series_scan(cudaStream_t st, const uint32_t *nsb, const uint32_t *npb, uint32_t *sbase, uint32_t B,
@@ -1037,7 +1052,13 @@ cudaError_t launch_detect_ewma(cudaStream_t st, const SeriesEntry *entries, cons
 {
     if (S == 0) return cudaSuccess;
     constexpr int NT = 128;
-    detect_ewma_kernel<NT><<<(S + NT - 1) / NT, NT, 0, st>>>(entries, offsets, sbase, B, S, csr_v, csr_t, out, out_cap, stats,
+    static int pad = -1;
+    if (pad < 0) {
+        const char *e = getenv("TAD_DETECT_SMEM");
+        pad = e ? atoi(e) : 0;
+        if (pad > 0) cudaFuncSetAttribute(detect_ewma_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
+    }
+    detect_ewma_kernel<NT><<<(S + NT - 1) / NT, NT, pad, st>>>(entries, offsets, sbase, B, S, csr_v, csr_t, out, out_cap, stats,
                                                             emit_all);
     return cudaGetLastError();
 }

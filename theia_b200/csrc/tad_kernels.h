@@ -16,8 +16,8 @@ size_t scan_sync_bytes();   // zero-initialised once; epoch must be > 0 and diff
 // `offsets` are the (virtual, contiguous) bucket offsets used for entries / csr arrays; the rows
 // themselves are read through `seg`.
 cudaError_t launch_group(cudaStream_t st, const SegDesc &seg, SeriesEntry *entries, const uint32_t *offsets, uint32_t B,
-                         int logB, uint64_t *csr_v, uint32_t *csr_t, uint32_t *csr_p, uint32_t *nsb, uint32_t *npb,
-                         int reducer);
+                         int logB, uint32_t max_bucket, uint64_t *csr_v, uint32_t *csr_t, uint32_t *csr_p, uint32_t *nsb,
+                         uint32_t *npb, int reducer, int *launches);
 cudaError_t launch_series_scan(cudaStream_t st, const uint32_t *nsb, const uint32_t *npb, uint32_t *sbase, uint32_t B,
                                uint32_t *stats, void *scan_sync, uint32_t epoch);
 cudaError_t launch_detect_ewma(cudaStream_t st, const SeriesEntry *entries, const uint32_t *offsets, const uint32_t *sbase, uint32_t B,

@@ -11,7 +11,7 @@ import numpy as np
 M1 = np.uint64(0xff51afd7ed558ccd)
 M2 = np.uint64(0xc4ceb9fe1a85ec53)
 GOLD = np.uint64(0x9e3779b97f4a7c15)
-GROUP_CAP = 2048
+GROUP_TARGET = 768
 
 
 def mix64(x: np.ndarray) -> np.ndarray:
@@ -39,7 +39,7 @@ def key_hash(table: dict) -> np.ndarray:
 
 
 def pick_logb(total_rows: int, world: int = 1) -> int:
-    target = GROUP_CAP * 3 // 8
+    target = GROUP_TARGET
     logb = 0
     while logb < 22 and (total_rows >> logb) > target:
         logb += 1
