@@ -72,7 +72,7 @@ struct tad_ctx {
     int num_sms = 148;
     // device workspace (grow-only, reused across jobs; jobs are serialized by the worker)
     DevBuf d_col[10], hist, offsets, cursor, big_list, big_base, csr_p, stats, part, csr_v, csr_t, nsb, npb, sbase, outb, ns_ignore, spill,
-        dbx, dbi, exch, scan_sync, small, hist_all, seg_off, seg_total, entries;
+        dbx, dbi, exch, scan_sync, small, hist_all, seg_off, seg_total, entries, ar_y, ar_pred, ar_lam;
     unsigned long long *h_small = nullptr;   // pinned, 64 x u64
     uint32_t scan_epoch = 0;
     uint32_t *h_stats = nullptr;   // pinned readback of the device scalars
@@ -514,6 +514,14 @@ void run_job(tad_ctx *ctx, tad_job *job)
             CU(launch_detect_dbscan(st, entries, offsets, sbase, Bl, S, csr_v, csr_t, csr_p, (uint32_t *)ctx->dbx.p,
                                     (uint8_t *)ctx->dbi.p, oc, (uint32_t)out_cap, d_stats, emit_all));
             launches += S ? 1 : 0;
+        } else if (sp.algo == TAD_ALGO_ARIMA) {
+            ensure(ctx->ar_y, cap_rows * 8);
+            ensure(ctx->ar_pred, cap_rows * 8);
+            ensure(ctx->ar_lam, ((size_t)S + 1) * 8);
+            CU(launch_detect_arima(st, entries, offsets, sbase, Bl, S, csr_v, csr_t, (double *)ctx->ar_y.p,
+                                   (double *)ctx->ar_pred.p, (double *)ctx->ar_lam.p, attempt == 0, oc, (uint32_t)out_cap,
+                                   d_stats, emit_all));
+            launches += S ? (attempt == 0 ? 3 : 1) : 0;
         } else {
             fail(TAD_ERR_UNSUPPORTED, "algorithm %d is not implemented by this build", sp.algo);
         }
@@ -724,7 +732,7 @@ void tad_shutdown(tad_ctx *ctx)
     DevBuf *bufs[] = {&ctx->hist, &ctx->offsets, &ctx->cursor, &ctx->big_list, &ctx->big_base, &ctx->csr_p, &ctx->stats, &ctx->part, &ctx->csr_v,
                       &ctx->csr_t, &ctx->nsb, &ctx->npb, &ctx->sbase, &ctx->outb, &ctx->ns_ignore, &ctx->spill, &ctx->dbx,
                       &ctx->dbi, &ctx->exch, &ctx->scan_sync, &ctx->small, &ctx->hist_all, &ctx->seg_off, &ctx->seg_total,
-                      &ctx->entries};
+                      &ctx->entries, &ctx->ar_y, &ctx->ar_pred, &ctx->ar_lam};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     for (int i = 0; i < 10; i++)

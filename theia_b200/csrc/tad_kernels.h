@@ -28,6 +28,13 @@ cudaError_t launch_detect_dbscan(cudaStream_t st, const SeriesEntry *entries, co
                                  uint32_t *scratch_pc, uint8_t *scratch_flag, const OutCols &out, uint32_t out_cap,
                                  uint32_t *stats, int emit_all);
 
+// ARIMA (tad_arima.cu): Box-Cox + per-prefix ARIMA(1,1,1) MLE fits (when `fit`) then score/flag/compact.
+// scratch_y / scratch_pred: one double per point slot; scratch_lam: one double per series.
+cudaError_t launch_detect_arima(cudaStream_t st, const SeriesEntry *entries, const uint32_t *offsets, const uint32_t *sbase,
+                                uint32_t B, uint32_t S, const uint64_t *csr_v, const uint32_t *csr_t, double *scratch_y,
+                                double *scratch_pred, double *scratch_lam, bool fit, const OutCols &out, uint32_t out_cap,
+                                uint32_t *stats, int emit_all);
+
 // Oversized buckets (more rows than the shared-memory capacity): global-memory path.
 // Sorts the rows of all listed buckets by (hash, key, time), reduces duplicates and writes the
 // same per-series arrays / in-place series entries / nsb / npb the group kernel produces.
