@@ -173,6 +173,9 @@ void tad_shutdown(tad_ctx *ctx);
 /* Replaces: the JDBC read target (anomaly_detection.py:655-662).  Allocates library-owned
  * pinned host (mem = TAD_MEM_HOST) or device (TAD_MEM_DEVICE) column buffers. */
 int tad_alloc_columns(tad_ctx *ctx, uint64_t capacity, int32_t mem, tad_columns *cols);
+/* Adds the two optional namespace-id columns (src_ns, dst_ns) to buffers obtained from
+ * tad_alloc_columns; needed only when the job carries an ns_ignore list (anomaly_detection.py:576-580). */
+int tad_alloc_ns_columns(tad_ctx *ctx, tad_columns *cols);
 int tad_free_columns(tad_ctx *ctx, tad_columns *cols);
 
 /* Replaces: CreateSparkApplication (controller.go:685, pkg/controller/util.go:223-233).

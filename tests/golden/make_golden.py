@@ -8,6 +8,8 @@ Run in the build container only (needs /root/reference):
 Writes
   tests/golden/reference_test_vectors.json -- the vectors the reference's own unit
       test holds (plugins/anomaly-detection/anomaly_detection_test.py:199-402).
+  tests/golden/sql_cases.json -- the 12 (arguments, SQL text) cases of the reference's SQL-generation test
+      (anomaly_detection_test.py:46-195).
   tests/golden/udf_cases.json -- seeded input series and the outputs of the
       reference UDFs ``calculate_ewma``, ``calculate_ewma_anomaly`` and
       ``calculate_dbscan_anomaly`` (anomaly_detection.py:146-212, 325-349) on them,
@@ -83,6 +85,13 @@ def main():
                    "reference_commit": "bc06ff0afe05c984f2efc7a53e68e8f152914c3e",
                    "cases": cases}, f)
     print("wrote %d udf cases" % len(cases))
+    # the reference's 12 SQL-generation cases (anomaly_detection_test.py:46-195): inputs + expected SQL text
+    import importlib
+    tmod = importlib.import_module("anomaly_detection_test")
+    sql_cases = [{"args": list(inp), "sql": sql} for inp, sql in tmod.test_generate_sql_query.pytestmark[0].args[1]]
+    with open(os.path.join(HERE, "sql_cases.json"), "w") as f:
+        json.dump(sql_cases, f, indent=1)
+    print("wrote %d sql cases" % len(sql_cases))
 
 
 if __name__ == "__main__":

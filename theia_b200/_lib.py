@@ -19,7 +19,7 @@ TAD_REDUCE_MAX, TAD_REDUCE_SUM = 0, 1
 
 EXPORTS = ("tad_abi_version", "tad_strerror", "tad_init", "tad_shutdown", "tad_alloc_columns",
            "tad_free_columns", "tad_submit", "tad_poll", "tad_wait", "tad_result", "tad_cancel",
-           "tad_release", "tad_get_unique_id")
+           "tad_release", "tad_get_unique_id", "tad_alloc_ns_columns")
 
 
 class TadConfig(C.Structure):
@@ -74,6 +74,7 @@ def load():
     L.tad_shutdown.restype = None
     L.tad_alloc_columns.argtypes = [C.c_void_p, C.c_uint64, C.c_int32, C.POINTER(TadColumns)]
     L.tad_free_columns.argtypes = [C.c_void_p, C.POINTER(TadColumns)]
+    L.tad_alloc_ns_columns.argtypes = [C.c_void_p, C.POINTER(TadColumns)]
     L.tad_submit.argtypes = [C.c_void_p, C.POINTER(TadJobSpec), C.POINTER(TadColumns), C.POINTER(C.c_void_p)]
     L.tad_poll.argtypes = [C.c_void_p, C.POINTER(TadStatus)]
     L.tad_wait.argtypes = [C.c_void_p, C.c_int64, C.POINTER(TadStatus)]

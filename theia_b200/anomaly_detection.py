@@ -1,0 +1,358 @@
+"""Host-side mirror of the reference job's interface (plugins/anomaly-detection/anomaly_detection.py),
+on top of the C ABI.  What the Go shim of INTEGRATION.md does, written in the language the reference job
+is written in, so the parity tests read like the reference's own tests.
+
+reference                               here
+--------------------------------------  ------------------------------------------------------------
+generate_tad_sql_query (:507-614)       plan_query() -> QueryPlan: WHERE predicate, key columns, reducer;
+                                        QueryPlan.to_sql() renders the reference's SQL text (pinned to
+                                        the reference's 12 SQL test cases) for ClickHouse push-down
+anomaly_detection (:647-710)            anomaly_detection(): plan -> host string predicates + dictionary
+                                        encoding -> tad_submit / tad_wait / tad_result -> tadetector rows
+filter_df_with_true_anomalies (:352-421) _result_rows(): per-aggregation column sets + the sentinel row
+remove_meaningless_labels (:631-644)    remove_meaningless_labels()
+main()/getopt (:729-900)                parse_args(): same long options (and the controller's spelling
+                                        --ns-ignore-list, which the reference's getopt rejects)
+
+Flow tables are dicts of numpy arrays named like the ClickHouse ``flows`` columns
+(build/charts/theia/provisioning/datasources/create_table.sh:31-85); IPs may be dotted strings or u32.
+All numeric work happens on the GPU; strings never leave the host (they become dictionary ids).
+"""
+from __future__ import annotations
+
+import calendar
+import getopt
+import json
+import time
+from dataclasses import dataclass, field
+from datetime import datetime
+
+import numpy as np
+
+from . import _lib as L
+
+TABLE_NAME = "default.flows"
+MEANINGLESS_LABELS = ("pod-template-hash", "controller-revision-hash", "pod-template-generation")
+VALID_ALGOS = ("EWMA", "ARIMA", "DBSCAN")
+KEY_SLOTS = ("src_ip", "src_port", "dst_ip", "dst_port", "proto", "flow_start")
+
+# per-connection query (anomaly_detection.py:52-61, 109-116)
+_CONN_SELECT = ["sourceIP", "sourceTransportPort", "destinationIP", "destinationTransportPort", "protocolIdentifier",
+                "flowStartSeconds", "flowEndSeconds", "max(throughput)"]
+_CONN_GROUP = ["sourceIP", "sourceTransportPort", "destinationIP", "destinationTransportPort", "protocolIdentifier",
+               "flowStartSeconds"]
+
+
+def remove_meaningless_labels(pod_labels: str) -> str:
+    """anomaly_detection.py:631-644."""
+    try:
+        d = json.loads(pod_labels)
+    except Exception:
+        return ""
+    return json.dumps({k: v for k, v in d.items() if k not in MEANINGLESS_LABELS}, sort_keys=True)
+
+
+def _sql_list(names):
+    return ", ".join("'{}'".format(x) for x in names)
+
+
+@dataclass
+class Branch:
+    """One SELECT of the (possibly UNION ALL) stage-A query."""
+    select: list
+    where: list                      # SQL condition strings, joined by the caller
+    group: list
+    key: dict = field(default_factory=dict)      # key slot -> flows column (or ('const', code))
+    direction: str = ""
+
+
+@dataclass
+class QueryPlan:
+    agg_flow: str
+    branches: list
+    reducer: int
+    ns_ignore: list
+    start_time: str
+    end_time: str
+    pod_sql_extension: str = ""
+
+    def to_sql(self) -> str:
+        """The text generate_tad_sql_query returns (anomaly_detection.py:507-614)."""
+        if self.agg_flow == "pod":
+            parts = []
+            for b in self.branches:
+                parts.append("(SELECT {} FROM {} WHERE {} {} GROUP BY {}) ".format(
+                    ", ".join(b.select), TABLE_NAME, b.where[0], self.pod_sql_extension, ", ".join(b.group)))
+            return "SELECT * FROM " + "UNION ALL ".join(parts)
+        b = self.branches[0]
+        sql = "SELECT {} FROM {} ".format(", ".join(b.select), TABLE_NAME)
+        if b.where:
+            sql += "WHERE " + " AND ".join(b.where) + " "
+        return sql + "GROUP BY {} ".format(", ".join(b.group))
+
+
+def plan_query(start_time="", end_time="", ns_ignore_list=(), agg_flow=None, pod_label=None, external_ip=None,
+               svc_port_name=None, pod_name=None, pod_namespace=None) -> QueryPlan:
+    """Same decisions as generate_tad_sql_query, as data instead of text."""
+    ns_ignore_list = list(ns_ignore_list or [])
+    if agg_flow == "pod":
+        second = "podLabels"
+        if pod_label:
+            inbound = "ilike(destinationPodLabels, '%{}%') ".format(pod_label)
+            outbound = "ilike(sourcePodLabels, '%{}%')".format(pod_label)
+            if pod_namespace:
+                inbound += " AND destinationPodNamespace = '{}'".format(pod_namespace)
+                outbound += " AND sourcePodNamespace = '{}'".format(pod_namespace)
+        elif pod_name:
+            inbound = "destinationPodName = '{}'".format(pod_name)
+            outbound = "sourcePodName = '{}'".format(pod_name)
+            if pod_namespace:
+                inbound += " AND destinationPodNamespace = '{}'".format(pod_namespace)
+                outbound += " AND sourcePodNamespace = '{}'".format(pod_namespace)
+            second = "podName"
+        else:
+            inbound = "destinationPodLabels <> '' "
+            outbound = "sourcePodLabels <> ''"
+        src_second = "PodLabels" if second == "podLabels" else "PodName"
+        ext = ("AND sourcePodNamespace NOT IN ({0}) AND destinationPodNamespace NOT IN ({0})".format(
+            _sql_list(ns_ignore_list)) if ns_ignore_list else "")
+        group = ["podNamespace", second, "direction", "flowEndSeconds"]
+        branches = [
+            Branch(["destinationPodNamespace AS podNamespace", "destination%s AS %s" % (src_second, second),
+                    "'inbound' AS direction", "flowEndSeconds", "sum(throughput)"], [inbound], group,
+                   {"src_ip": "destinationPodNamespace", "dst_ip": "destination" + src_second, "proto": ("const", 0)},
+                   "inbound"),
+            Branch(["sourcePodNamespace AS podNamespace", "source%s AS %s" % (src_second, second),
+                    "'outbound' AS direction", "flowEndSeconds", "sum(throughput)"], [outbound], group,
+                   {"src_ip": "sourcePodNamespace", "dst_ip": "source" + src_second, "proto": ("const", 1)},
+                   "outbound"),
+        ]
+        return QueryPlan("pod", branches, L.TAD_REDUCE_SUM, ns_ignore_list, "", "", ext)
+
+    where = []
+    if ns_ignore_list:
+        where.append("sourcePodNamespace NOT IN ({0}) AND destinationPodNamespace NOT IN ({0})".format(
+            _sql_list(ns_ignore_list)))
+    if start_time:
+        where.append("flowStartSeconds >= '{}'".format(start_time))
+    if end_time:
+        where.append("flowEndSeconds < '{}'".format(end_time))
+    if agg_flow == "external":
+        where.append("flowType = 3")
+        if external_ip:
+            where.append("destinationIP = '{}'".format(external_ip))
+        b = Branch(["destinationIP", "flowType", "flowEndSeconds", "sum(throughput)"], where,
+                   ["destinationIP", "flowType", "flowEndSeconds"], {"dst_ip": "destinationIP", "proto": "flowType"})
+        return QueryPlan("external", [b], L.TAD_REDUCE_SUM, ns_ignore_list, start_time, end_time)
+    if agg_flow == "svc":
+        where.append("destinationServicePortName = '{}'".format(svc_port_name) if svc_port_name
+                     else "destinationServicePortName <> ''")
+        b = Branch(["destinationServicePortName", "flowEndSeconds", "sum(throughput)"], where,
+                   ["destinationServicePortName", "flowEndSeconds"], {"src_ip": "destinationServicePortName"})
+        return QueryPlan("svc", [b], L.TAD_REDUCE_SUM, ns_ignore_list, start_time, end_time)
+    b = Branch(list(_CONN_SELECT), where, _CONN_GROUP + ["flowEndSeconds"],
+               {"src_ip": "sourceIP", "src_port": "sourceTransportPort", "dst_ip": "destinationIP",
+                "dst_port": "destinationTransportPort", "proto": "protocolIdentifier", "flow_start": "flowStartSeconds"})
+    return QueryPlan(agg_flow or "", [b], L.TAD_REDUCE_MAX, ns_ignore_list, start_time, end_time)
+
+
+# ------------------------------------------------------------------------------------------------
+def _epoch(ts: str) -> int:
+    """'YYYY-MM-DD hh:mm:ss' (UTC, anomaly_detection.py:754-762) -> epoch seconds; '' -> 0."""
+    return calendar.timegm(datetime.strptime(ts, "%Y-%m-%d %H:%M:%S").timetuple()) if ts else 0
+
+
+def ip_to_u32(col) -> np.ndarray:
+    a = np.asarray(col)
+    if a.dtype.kind in "iu":
+        return a.astype(np.uint32)
+    out = np.empty(len(a), dtype=np.uint32)
+    for i, s in enumerate(a):
+        p = str(s).split(".")
+        out[i] = (int(p[0]) << 24) | (int(p[1]) << 16) | (int(p[2]) << 8) | int(p[3])
+    return out
+
+
+def u32_to_ip(v: int) -> str:
+    return "%d.%d.%d.%d" % ((v >> 24) & 255, (v >> 16) & 255, (v >> 8) & 255, v & 255)
+
+
+class Dictionary:
+    """string -> dense id (and back); what the shim keeps per job for non-numeric key columns."""
+
+    def __init__(self):
+        self.ids, self.names = {}, []
+
+    def encode(self, col) -> np.ndarray:
+        out = np.empty(len(col), dtype=np.uint32)
+        for i, s in enumerate(col):
+            s = str(s)
+            j = self.ids.get(s)
+            if j is None:
+                j = self.ids[s] = len(self.names)
+                self.names.append(s)
+            out[i] = j
+        return out
+
+
+def _host_mask(flows: dict, plan: QueryPlan, branch: Branch, pod_label, pod_name, pod_namespace, external_ip,
+               svc_port_name) -> np.ndarray:
+    """String predicates of the WHERE clause (time window and namespace ignore list run on the GPU)."""
+    n = len(flows["flowEndSeconds"])
+    m = np.ones(n, dtype=bool)
+    if plan.agg_flow == "pod":
+        side = "destination" if branch.direction == "inbound" else "source"
+        if pod_label:
+            lab = np.asarray(flows[side + "PodLabels"]).astype(str)
+            m &= np.char.find(np.char.lower(lab), pod_label.lower()) >= 0        # ilike '%label%'
+        elif pod_name:
+            m &= np.asarray(flows[side + "PodName"]).astype(str) == pod_name
+        else:
+            m &= np.asarray(flows[side + "PodLabels"]).astype(str) != ""
+        if pod_namespace and (pod_label or pod_name):
+            m &= np.asarray(flows[side + "PodNamespace"]).astype(str) == pod_namespace
+    elif plan.agg_flow == "external":
+        m &= np.asarray(flows["flowType"]) == 3
+        if external_ip:
+            m &= ip_to_u32(flows["destinationIP"]) == ip_to_u32([external_ip])[0]
+    elif plan.agg_flow == "svc":
+        svc = np.asarray(flows["destinationServicePortName"]).astype(str)
+        m &= (svc == svc_port_name) if svc_port_name else (svc != "")
+    return m
+
+
+def anomaly_detection(engine, algo_type: str, flows: dict, start_time: str = "", end_time: str = "", tad_id: str = "",
+                      ns_ignore_list=(), agg_flow=None, pod_label=None, external_ip=None, svc_port_name=None,
+                      pod_name=None, pod_namespace=None, now=None):
+    """anomaly_detection.py:647-710 + write_anomaly_detection_result (:713-726): returns the list of row dicts the
+    reference appends to default.tadetector (one sentinel row when nothing is anomalous) and the job status."""
+    if algo_type not in VALID_ALGOS:
+        raise ValueError("Algorithm should be in {}".format(" or ".join(VALID_ALGOS)))      # :811-818
+    plan = plan_query(start_time, end_time, ns_ignore_list, agg_flow, pod_label, external_ip, svc_port_name, pod_name,
+                      pod_namespace)
+    dicts = {slot: Dictionary() for slot in KEY_SLOTS}
+    ns_dict = Dictionary()
+    parts = []
+    for br in plan.branches:
+        mask = _host_mask(flows, plan, br, pod_label, pod_name, pod_namespace, external_ip, svc_port_name)
+        idx = np.flatnonzero(mask)
+        cols = {}
+        for slot in KEY_SLOTS:
+            src = br.key.get(slot)
+            if src is None:
+                cols[slot] = None
+            elif isinstance(src, tuple):
+                cols[slot] = np.full(len(idx), src[1], dtype=np.uint32)
+            else:
+                raw = np.asarray(flows[src])[idx]
+                if src in ("sourceIP", "destinationIP"):
+                    cols[slot] = ip_to_u32(raw)
+                elif raw.dtype.kind in "iu":
+                    cols[slot] = raw
+                else:
+                    cols[slot] = dicts[slot].encode(raw)
+        cols["flow_end"] = np.asarray(flows["flowEndSeconds"])[idx]
+        cols["value"] = np.asarray(flows["throughput"])[idx]
+        if plan.ns_ignore:
+            cols["src_ns"] = ns_dict.encode(np.asarray(flows["sourcePodNamespace"])[idx])
+            cols["dst_ns"] = ns_dict.encode(np.asarray(flows["destinationPodNamespace"])[idx])
+        parts.append(cols)
+    table = {}
+    for k in parts[0]:
+        if any(p[k] is None for p in parts):
+            table[k] = None
+        else:
+            table[k] = np.concatenate([np.asarray(p[k]) for p in parts])
+    ignore_ids = [ns_dict.ids[n] for n in plan.ns_ignore if n in ns_dict.ids]
+    got, st = engine.run(table, algo=algo_type, reducer=plan.reducer, start_time=_epoch(plan.start_time),
+                         end_time=_epoch(plan.end_time), tad_id=tad_id, ns_ignore=ignore_ids)
+    return _result_rows(got, plan, dicts, algo_type, tad_id, pod_label, now), st
+
+
+def _result_rows(got: dict, plan: QueryPlan, dicts: dict, algo_type: str, tad_id: str, pod_label, now=None) -> list:
+    """filter_df_with_true_anomalies' projections (anomaly_detection.py:359-393), the string cast of ``anomaly``
+    (:500-502), the ``id`` column (:503) and the sentinel row (:395-420)."""
+    agg_type = plan.agg_flow if plan.agg_flow else "None"
+    rows = []
+    for i in range(len(got["flow_end"])):
+        common = {"aggType": agg_type, "flowEndSeconds": int(got["flow_end"][i]),
+                  "throughputStandardDeviation": float(got["stddev"][i]), "algoType": algo_type,
+                  "algoCalc": float(got["algo_calc"][i]), "throughput": float(got["throughput"][i]),
+                  "anomaly": "true", "id": tad_id}
+        if plan.agg_flow == "pod":
+            second = dicts["dst_ip"].names[int(got["dst_ip"][i])]
+            row = {"podNamespace": dicts["src_ip"].names[int(got["src_ip"][i])],
+                   "direction": "inbound" if int(got["proto"][i]) == 0 else "outbound"}
+            if plan.branches[0].group[1] == "podLabels":
+                row["podLabels"] = remove_meaningless_labels(second)          # :687-695
+            else:
+                row["podName"] = second
+        elif plan.agg_flow == "external":
+            row = {"destinationIP": u32_to_ip(int(got["dst_ip"][i]))}
+        elif plan.agg_flow == "svc":
+            row = {"destinationServicePortName": dicts["src_ip"].names[int(got["src_ip"][i])]}
+        else:
+            row = {"sourceIP": u32_to_ip(int(got["src_ip"][i])), "sourceTransportPort": int(got["src_port"][i]),
+                   "destinationIP": u32_to_ip(int(got["dst_ip"][i])),
+                   "destinationTransportPort": int(got["dst_port"][i]), "protocolIdentifier": int(got["proto"][i]),
+                   "flowStartSeconds": int(got["flow_start"][i])}
+        row.update(common)
+        rows.append(row)
+    if not rows:
+        rows.append({
+            "sourceIP": "None", "sourceTransportPort": 0, "destinationIP": "None", "destinationTransportPort": 0,
+            "protocolIdentifier": 0,
+            "flowStartSeconds": (now or datetime.now()).strftime("%Y-%m-%d %H:%M:%S"),
+            "podNamespace": "None", "podLabels": "None", "podName": "None", "destinationServicePortName": "None",
+            "direction": "None", "flowEndSeconds": 0, "throughputStandardDeviation": 0, "aggType": agg_type,
+            "algoType": algo_type, "algoCalc": 0.0, "throughput": 0.0, "anomaly": "NO ANOMALY DETECTED", "id": tad_id})
+    return rows
+
+
+def parse_args(argv):
+    """The job's command line (anomaly_detection.py:781-870).  Accepts the reference's long options AND the
+    spelling the controller actually passes (--ns-ignore-list, controller.go:546), which the reference's
+    getopt rejects with exit code 2 -- a reference bug this engine does not reproduce."""
+    opts, _ = getopt.getopt(argv, "ht:d:s:e:i:n:f:l:x:p:N:P:", [
+        "help", "algo=", "db_jdbc_url=", "start_time=", "end_time=", "id=", "ns_ignore_list=", "ns-ignore-list=",
+        "agg-flow=", "pod-label=", "external-ip=", "svc-port-name=", "pod-name=", "pod-namespace="])
+    out = {"algo": "", "start_time": "", "end_time": "", "id": None, "ns_ignore_list": [], "agg_flow": "",
+           "pod_label": "", "external_ip": "", "svc_port_name": "", "pod_name": "", "pod_namespace": ""}
+    for opt, arg in opts:
+        if opt in ("-a", "--algo"):
+            if arg not in VALID_ALGOS:
+                raise SystemExit(2)
+            out["algo"] = arg
+        elif opt in ("-s", "--start_time", "-e", "--end_time"):
+            try:
+                datetime.strptime(arg, "%Y-%m-%d %H:%M:%S")
+            except ValueError:
+                raise SystemExit(2)
+            out["start_time" if opt in ("-s", "--start_time") else "end_time"] = arg
+        elif opt in ("-n", "--ns_ignore_list", "--ns-ignore-list"):
+            lst = json.loads(arg)
+            if not isinstance(lst, list):
+                raise SystemExit(2)
+            out["ns_ignore_list"] = lst
+        elif opt in ("-i", "--id"):
+            out["id"] = arg
+        elif opt in ("-f", "--agg-flow"):
+            out["agg_flow"] = arg
+        elif opt in ("-l", "--pod-label"):
+            out["pod_label"] = arg
+        elif opt in ("-N", "--pod-name"):
+            out["pod_name"] = arg
+        elif opt in ("-P", "--pod-namespace"):
+            out["pod_namespace"] = arg
+        elif opt in ("-x", "--external-ip"):
+            out["external_ip"] = arg
+        elif opt in ("-p", "--svc-port-name"):
+            out["svc_port_name"] = arg
+    return out
+
+
+def timed_job(engine, *args, **kw):
+    """main()'s only timing hook: 'Anomaly Detection completed, id: {}, in {} seconds' (anomaly_detection.py:872-899)."""
+    t0 = time.time()
+    rows, st = anomaly_detection(engine, *args, **kw)
+    return rows, st, time.time() - t0

@@ -771,6 +771,23 @@ int tad_alloc_columns(tad_ctx *ctx, uint64_t capacity, int32_t mem, tad_columns 
     return TAD_OK;
 }
 
+int tad_alloc_ns_columns(tad_ctx *ctx, tad_columns *cols)
+{
+    if (!ctx || !cols || !cols->capacity) return TAD_ERR_INVALID_ARG;
+    if (cudaSetDevice(ctx->cfg.device) != cudaSuccess) return TAD_ERR_CUDA;
+    void **slots[2] = {(void **)&cols->src_ns, (void **)&cols->dst_ns};
+    for (int i = 0; i < 2; i++) {
+        if (*slots[i]) continue;
+        const size_t bytes = (cols->capacity * 4 + 255) & ~size_t(255);
+        cudaError_t e = cols->mem == TAD_MEM_HOST ? cudaHostAlloc(slots[i], bytes, cudaHostAllocDefault) : cudaMalloc(slots[i], bytes);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return TAD_ERR_NOMEM;
+        }
+    }
+    return TAD_OK;
+}
+
 int tad_free_columns(tad_ctx *ctx, tad_columns *cols)
 {
     if (!ctx || !cols) return TAD_ERR_INVALID_ARG;

@@ -17,6 +17,7 @@ from . import _lib as L
 
 _COLS = (("src_ip", np.uint32), ("dst_ip", np.uint32), ("src_port", np.uint16), ("dst_port", np.uint16),
          ("proto", np.uint8), ("flow_start", np.uint32), ("flow_end", np.uint32), ("value", np.uint64))
+_NS_COLS = (("src_ns", np.uint32), ("dst_ns", np.uint32))
 _OUT = (("src_ip", np.uint32), ("dst_ip", np.uint32), ("src_port", np.uint16), ("dst_port", np.uint16),
         ("proto", np.uint8), ("flow_start", np.uint32), ("flow_end", np.uint32), ("stddev", np.float64),
         ("algo_calc", np.float64), ("throughput", np.float64), ("anomaly", np.uint8))
@@ -53,7 +54,7 @@ class Columns:
     def view(self, name: str) -> np.ndarray:
         """numpy view of a host column (capacity elements)."""
         assert self.c.mem == L.TAD_MEM_HOST
-        dt = dict(_COLS)[name]
+        dt = dict(_COLS + _NS_COLS)[name]
         n = int(self.c.capacity)
         ptr = getattr(self.c, name)
         buf = (C.c_char * (n * np.dtype(dt).itemsize)).from_address(ptr)
@@ -68,6 +69,13 @@ class Columns:
                 self.view(name)[:n] = 0
             else:
                 self.view(name)[:n] = np.asarray(a, dtype=dt)
+        if table.get("src_ns") is not None or table.get("dst_ns") is not None:
+            rc = self.eng.lib.tad_alloc_ns_columns(self.eng.ctx, C.byref(self.c))
+            if rc != 0:
+                raise TadError(rc, "tad_alloc_ns_columns")
+            for name, dt in _NS_COLS:
+                a = table.get(name)
+                self.view(name)[:n] = 0 if a is None else np.asarray(a, dtype=dt)
         self.c.rows = n
         return self
 
