@@ -702,6 +702,28 @@ __device__ __forceinline__ uint32_t find_bucket(const uint32_t *__restrict__ sba
     return lo;
 }
 
+// Bucket of series `i` for every thread of a CTA whose threads hold consecutive series: one thread searches
+// the bucket of the CTA's first series, a window of sbase[] starting there is staged in shared memory, and
+// each thread finishes with a short search inside the window (global binary search only if it falls outside).
+constexpr int kBucketWindow = 256;
+__device__ __forceinline__ uint32_t find_bucket_cta(const uint32_t *__restrict__ sbase, uint32_t B, uint32_t i, uint32_t i_first,
+                                                    uint32_t *win /* kBucketWindow + 1 */, uint32_t *b0_s)
+{
+    if (threadIdx.x == 0) *b0_s = find_bucket(sbase, B, i_first);
+    __syncthreads();
+    const uint32_t b0 = *b0_s;
+    for (uint32_t k = threadIdx.x; k <= (uint32_t)kBucketWindow; k += blockDim.x)
+        win[k] = b0 + k <= B ? sbase[b0 + k] : 0xffffffffu;
+    __syncthreads();
+    if (win[kBucketWindow] <= i) return find_bucket(sbase, B, i);      // beyond the window (many empty buckets)
+    uint32_t lo = 0, hi = kBucketWindow;                                // win[lo] <= i < win[hi]
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (win[mid] <= i) lo = mid; else hi = mid;
+    }
+    return b0 + lo;
+}
+
 __device__ __forceinline__ void write_out(const OutCols &o, uint32_t idx, const SeriesEntry &e, uint32_t t, double sd,
                                           double calc, double x, bool flag)
 {
@@ -736,21 +758,99 @@ __device__ __forceinline__ void for_each_value(const uint64_t *__restrict__ v, u
     for (; i < n; i++) f(v[i], i);
 }
 
-// stddev_samp as Spark's CentralMomentAgg computes it (Welford), sequential in time order.
+// Division by the running count on the Welford critical path.  d / k with k a small integer is computed as
+// q0 = d * r, two FMA residual corrections (r = RN(1/k) from a table filled with __drcp_rn).  With a correctly
+// rounded reciprocal the first correction yields a faithful quotient and the second the correctly rounded one
+// (Markstein's theorem; k < 2^53 - 1 never has an all-ones significand), so the result is bit-identical to
+// IEEE division -- checked against `/` on 6e8 random operands (profiles/microbench/divcheck.c) -- at a fifth of
+// the dependent latency of the generic __ddiv_rn sequence.
+constexpr uint32_t kRcpTable = 4096;
+__device__ double g_rcp[kRcpTable + 1];
+
+__global__ void rcp_table_kernel()
+{
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k <= kRcpTable) g_rcp[k] = k ? __drcp_rn((double)k) : 0.0;
+}
+
+__device__ __forceinline__ double div_by_count(double d, double cnt, uint32_t k)
+{
+    if (k <= kRcpTable) {
+        const double r = g_rcp[k];
+        const double q0 = __dmul_rn(d, r);
+        const double q1 = __fma_rn(__fma_rn(-cnt, q0, d), r, q0);
+        return __fma_rn(__fma_rn(-cnt, q1, d), r, q1);
+    }
+    return __ddiv_rn(d, cnt);
+}
+
+// stddev_samp as Spark's CentralMomentAgg computes it (Welford), sequential in time order.  The reciprocals
+// of the next four counts are fetched before the dependent chain of the current four values starts, so the
+// table load never sits on the critical path.
 __device__ __forceinline__ double series_stddev(const uint64_t *__restrict__ v, uint32_t n, bool &has_sd)
 {
     double cnt = 0.0, avg = 0.0, m2 = 0.0;
-    for_each_value(v, n, [&](uint64_t raw, uint32_t) {
+    auto step = [&](uint64_t raw, double r, bool have_r) {
         const double x = __ull2double_rn(raw);
         cnt = __dadd_rn(cnt, 1.0);
         const double d = __dsub_rn(x, avg);
-        const double dn = __ddiv_rn(d, cnt);
+        double dn;
+        if (have_r) {
+            const double q0 = __dmul_rn(d, r);
+            const double q1 = __fma_rn(__fma_rn(-cnt, q0, d), r, q0);
+            dn = __fma_rn(__fma_rn(-cnt, q1, d), r, q1);
+        } else {
+            dn = __ddiv_rn(d, cnt);
+        }
         avg = __dadd_rn(avg, dn);
         m2 = __dadd_rn(m2, __dmul_rn(d, __dsub_rn(d, dn)));
-    });
+    };
+    uint32_t i = 0;
+    const uint32_t mis = (uint32_t)((reinterpret_cast<uintptr_t>(v) >> 3) & 3u);
+    const uint32_t head = min(n, (4u - mis) & 3u);
+    for (; i < head; i++) step(v[i], g_rcp[min(i + 1u, kRcpTable)], i + 1u <= kRcpTable);
+    double r0 = 0, r1 = 0, r2 = 0, r3 = 0;
+    if (i + 4 <= n) {
+        r0 = g_rcp[min(i + 1u, kRcpTable)]; r1 = g_rcp[min(i + 2u, kRcpTable)];
+        r2 = g_rcp[min(i + 3u, kRcpTable)]; r3 = g_rcp[min(i + 4u, kRcpTable)];
+    }
+    for (; i + 4 <= n; i += 4) {
+        const ulonglong2 a = *reinterpret_cast<const ulonglong2 *>(v + i);
+        const ulonglong2 b = *reinterpret_cast<const ulonglong2 *>(v + i + 2);
+        const double c0 = r0, c1 = r1, c2 = r2, c3 = r3;
+        const bool ok = i + 4u <= kRcpTable;
+        // reciprocals of the NEXT group: independent of the chain below
+        r0 = g_rcp[min(i + 5u, kRcpTable)]; r1 = g_rcp[min(i + 6u, kRcpTable)];
+        r2 = g_rcp[min(i + 7u, kRcpTable)]; r3 = g_rcp[min(i + 8u, kRcpTable)];
+        step(a.x, c0, ok); step(a.y, c1, ok); step(b.x, c2, ok); step(b.y, c3, ok);
+    }
+    for (; i < n; i++) step(v[i], g_rcp[min(i + 1u, kRcpTable)], i + 1u <= kRcpTable);
     has_sd = n >= 2;
     return has_sd ? __dsqrt_rn(__ddiv_rn(m2, __dsub_rn(cnt, 1.0))) : __longlong_as_double(0x7ff8000000000000LL);
 }
+
+// The NT series of a CTA are consecutive in series order, hence (almost always) one contiguous span of
+// csr_v.  The span is staged in shared memory with ONE TMA bulk copy; every thread then runs two sequential
+// passes over its own series out of shared memory (Welford stddev; EWMA + flag).  Flagged points go into a
+// shared-memory queue and are written out cooperatively, one result row per thread, so each of the eleven
+// result columns is written coalesced.  Spans larger than the stage and queue overflows (TAD_FLAG_EMIT_ALL)
+// take the direct per-thread path.
+constexpr int kDetectThreads = 96;
+constexpr int kDetectStage = 10240;                   // staged u64 values per CTA
+constexpr int kDetectQueue = 1024;                    // queued result rows per CTA
+
+struct DetectSmem {
+    alignas(128) unsigned long long stage[kDetectStage];
+    double qcalc[kDetectQueue];
+    uint32_t qmeta[kDetectQueue];                     // bit 31: flag, bits 30..16: owning thread, low 16: unused
+    uint32_t qpos[kDetectQueue];                      // index of the point in csr_v / csr_t
+    unsigned long long ent_a[kDetectThreads], ent_b[kDetectThreads];
+    double ent_sd[kDetectThreads];
+    uint32_t ent_proto[kDetectThreads];
+    alignas(8) unsigned long long mbar;
+    uint32_t span_lo, span_hi, qcount, base, b0;
+    uint32_t win[kBucketWindow + 1];
+};
 
 template <int NT>
 __global__ void __launch_bounds__(NT) detect_ewma_kernel(const SeriesEntry *__restrict__ entries, const uint32_t *__restrict__ offsets,
@@ -758,49 +858,95 @@ __global__ void __launch_bounds__(NT) detect_ewma_kernel(const SeriesEntry *__re
                                                          const uint64_t *__restrict__ csr_v, const uint32_t *__restrict__ csr_t,
                                                          OutCols out, uint32_t out_cap, uint32_t *__restrict__ stats, int emit_all)
 {
-    __shared__ uint32_t warp_sums[32];
-    __shared__ uint32_t total_s, base_s;
+    extern __shared__ __align__(128) unsigned char detect_smem[];
+    DetectSmem &sm = *reinterpret_cast<DetectSmem *>(detect_smem);
     const uint32_t i = blockIdx.x * NT + threadIdx.x;
+    if (threadIdx.x == 0) {
+        sm.span_lo = 0xffffffffu;
+        sm.span_hi = 0u;
+        sm.qcount = 0u;
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&sm.mbar)), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
     SeriesEntry e;
-    e.n = 0;
-    const uint64_t *v = nullptr;
-    bool has_sd = false;
-    double sd = 0.0;
-    uint32_t count = 0;
+    e.n = 0; e.off = 0; e.a = 0; e.b = 0; e.proto = 0;
+    const uint32_t bkt = find_bucket_cta(sbase, B, i < S ? i : S - 1, blockIdx.x * NT, sm.win, &sm.b0);
     if (i < S) {
-        const uint32_t b = find_bucket(sbase, B, i);
+        const uint32_t b = bkt;
         const uint4 *p = reinterpret_cast<const uint4 *>(entries + offsets[b] + (i - sbase[b]));
         const uint4 k = p[0], w = p[1];
         e.a = pack64(k.x, k.y); e.b = pack64(k.z, k.w); e.proto = w.x; e.n = w.y; e.off = w.z;
-        v = csr_v + e.off;
+    }
+    {
+        const uint32_t lo = __reduce_min_sync(0xffffffffu, e.n ? e.off : 0xffffffffu);
+        const uint32_t hi = __reduce_max_sync(0xffffffffu, e.n ? e.off + e.n : 0u);
+        if ((threadIdx.x & 31) == 0) { atomicMin(&sm.span_lo, lo); atomicMax(&sm.span_hi, hi); }
+    }
+    __syncthreads();
+    const uint32_t lo_a = sm.span_lo & ~3u;                      // keep the 32-byte sector phase of csr_v
+    const bool staged = sm.span_hi > lo_a && sm.span_hi - lo_a <= (uint32_t)kDetectStage;
+    if (staged) {
+        if (threadIdx.x == 0) {
+            const uint32_t bytes = ((sm.span_hi - lo_a) * 8u + 15u) & ~15u;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(&sm.mbar)), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         :: "r"(smem_u32(sm.stage)), "l"(csr_v + lo_a), "r"(bytes), "r"(smem_u32(&sm.mbar)) : "memory");
+        }
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(smem_u32(&sm.mbar)), "r"(0) : "memory");
+        }
+    }
+    const uint64_t *v = staged ? reinterpret_cast<const uint64_t *>(sm.stage) + (e.off - lo_a) : csr_v + e.off;
+    bool has_sd = false;
+    double sd = 0.0;
+    if (e.n) {
         sd = series_stddev(v, e.n, has_sd);
-        if (emit_all) {
-            count = e.n;
-        } else if (has_sd) {
+        sm.ent_a[threadIdx.x] = e.a; sm.ent_b[threadIdx.x] = e.b; sm.ent_proto[threadIdx.x] = e.proto;
+        sm.ent_sd[threadIdx.x] = sd;
+        if (has_sd || emit_all) {
             double prev = 0.0;
-            for_each_value(v, e.n, [&](uint64_t raw, uint32_t) {
+            for_each_value(v, e.n, [&](uint64_t raw, uint32_t q) {
                 const double x = __ull2double_rn(raw);
                 prev = __dadd_rn(__dmul_rn(0.5, prev), __dmul_rn(0.5, x));
-                count += (fabs(__dsub_rn(x, prev)) > sd) ? 1u : 0u;
+                const bool flag = has_sd && (fabs(__dsub_rn(x, prev)) > sd);
+                if (flag || emit_all) {
+                    const uint32_t slot = atomicAdd(&sm.qcount, 1u);
+                    if (slot < (uint32_t)kDetectQueue) {
+                        sm.qcalc[slot] = prev;
+                        sm.qpos[slot] = e.off + q;
+                        sm.qmeta[slot] = (flag ? 0x80000000u : 0u) | (threadIdx.x << 16);
+                    } else {                                        // queue full: direct emission
+                        const uint32_t idx = atomicAdd(&stats[ST_OUTCOUNT], 1u);
+                        if (idx < out_cap) write_out(out, idx, e, csr_t[e.off + q], sd, prev, x, flag);
+                    }
+                }
             });
         }
     }
-    const uint32_t pre = block_exclusive_scan<NT>(count, warp_sums, &total_s);
-    if (threadIdx.x == 0) base_s = total_s ? atomicAdd(&stats[ST_OUTCOUNT], total_s) : 0u;
     __syncthreads();
-    if (count == 0) return;
-    uint32_t idx = base_s + pre;
-    const uint32_t *t = csr_t + e.off;
-    double prev = 0.0;
-    for_each_value(v, e.n, [&](uint64_t raw, uint32_t q) {
-        const double x = __ull2double_rn(raw);
-        prev = __dadd_rn(__dmul_rn(0.5, prev), __dmul_rn(0.5, x));
-        const bool flag = has_sd && (fabs(__dsub_rn(x, prev)) > sd);
-        if (flag || emit_all) {
-            if (idx < out_cap) write_out(out, idx, e, t[q], sd, prev, x, flag);
-            idx++;
-        }
-    });
+    const uint32_t nq = min(sm.qcount, (uint32_t)kDetectQueue);
+    if (threadIdx.x == 0) sm.base = nq ? atomicAdd(&stats[ST_OUTCOUNT], nq) : 0u;
+    __syncthreads();
+    for (uint32_t j = threadIdx.x; j < nq; j += NT) {
+        const uint32_t idx = sm.base + j;
+        if (idx >= out_cap) continue;
+        const uint32_t meta = sm.qmeta[j], pos = sm.qpos[j], owner = (meta >> 16) & 0x7fffu;
+        const uint64_t ka = sm.ent_a[owner], kb = sm.ent_b[owner];
+        out.src_ip[idx] = (uint32_t)(ka >> 32);
+        out.dst_ip[idx] = (uint32_t)ka;
+        out.flow_start[idx] = (uint32_t)(kb >> 32);
+        out.src_port[idx] = (uint16_t)(kb >> 16);
+        out.dst_port[idx] = (uint16_t)kb;
+        out.proto[idx] = (uint8_t)sm.ent_proto[owner];
+        out.flow_end[idx] = csr_t[pos];
+        out.stddev[idx] = sm.ent_sd[owner];
+        out.algo_calc[idx] = sm.qcalc[j];
+        out.throughput[idx] = __ull2double_rn(staged ? sm.stage[pos - lo_a] : csr_v[pos]);
+        out.anomaly[idx] = (meta >> 31) ? 1 : 0;
+    }
 }
 
 // ----------------------------------------------------------------------------------------
@@ -1046,20 +1192,31 @@ cudaError_t launch_series_scan(cudaStream_t st, const uint32_t *nsb, const uint3
     return cudaGetLastError();
 }
 
+static void ensure_rcp_table(cudaStream_t st)
+{
+    static bool done = false;
+    if (!done) {
+        rcp_table_kernel<<<(kRcpTable + 256) / 256, 256, 0, st>>>();
+        done = true;
+    }
+}
+
 cudaError_t launch_detect_ewma(cudaStream_t st, const SeriesEntry *entries, const uint32_t *offsets, const uint32_t *sbase, uint32_t B,
                                uint32_t S, const uint64_t *csr_v, const uint32_t *csr_t, const OutCols &out,
                                uint32_t out_cap, uint32_t *stats, int emit_all)
 {
     if (S == 0) return cudaSuccess;
-    constexpr int NT = 128;
-    static int pad = -1;
-    if (pad < 0) {
-        const char *e = getenv("TAD_DETECT_SMEM");
-        pad = e ? atoi(e) : 0;
-        if (pad > 0) cudaFuncSetAttribute(detect_ewma_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
+    constexpr int NT = kDetectThreads;
+    constexpr int smem = (int)sizeof(DetectSmem);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(detect_ewma_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
     }
-    detect_ewma_kernel<NT><<<(S + NT - 1) / NT, NT, pad, st>>>(entries, offsets, sbase, B, S, csr_v, csr_t, out, out_cap, stats,
-                                                            emit_all);
+    ensure_rcp_table(st);
+    detect_ewma_kernel<NT><<<(S + NT - 1) / NT, NT, smem, st>>>(entries, offsets, sbase, B, S, csr_v, csr_t, out, out_cap, stats,
+                                                               emit_all);
     return cudaGetLastError();
 }
 
@@ -1070,6 +1227,7 @@ cudaError_t launch_detect_dbscan(cudaStream_t st, const SeriesEntry *entries, co
 {
     if (S == 0) return cudaSuccess;
     constexpr int NT = 128;
+    ensure_rcp_table(st);
     detect_dbscan_kernel<NT><<<(S + NT - 1) / NT, NT, 0, st>>>(entries, offsets, sbase, B, S, csr_v, csr_t,
                                                               const_cast<uint32_t *>(csr_p), scratch_pc, scratch_flag, out,
                                                               out_cap, stats, emit_all);
