@@ -42,41 +42,74 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    """nvidia-smi clocks / throttle reasons: one streaming `nvidia-smi -lms 20` process; only the samples whose
+    timestamps fall inside the timed region are kept."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index=0):
-        self.index, self.samples, self.stop_flag, self.th = index, [], False, None
+        self.index, self.lines, self.proc, self.th = index, [], None, None
+        self.t0 = self.t1 = None
 
-    def _run(self):
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                f = [x.strip() for x in out.strip().split(",")]
-                if len(f) >= 6:
-                    self.samples.append(f)
-            except Exception:
-                pass
-            time.sleep(0.2)
+    def _pump(self):
+        try:
+            for line in self.proc.stdout:
+                self.lines.append((time.time(), line))
+        except Exception:
+            pass
 
     def start(self):
-        self.th = threading.Thread(target=self._run, daemon=True)
-        self.th.start()
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._pump, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
-        self.stop_flag = True
-        if self.th:
-            self.th.join(timeout=6)
-        if not self.samples:
+        if self.proc is not None:
+            time.sleep(0.05)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=3)
+            except Exception:
+                self.proc.kill()
+        rows = []
+        for ts, line in self.lines:
+            f = [x.strip() for x in line.strip().split(",")]
+            if len(f) >= 7:
+                rows.append((ts, f[1:]))
+        inside = [f for ts, f in rows if self.t0 is not None and self.t0 - 0.02 <= ts <= self.t1 + 0.02]
+        use = inside if inside else [f for _, f in rows[-3:]]
+        if not use:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        sm = sorted(int(f[0]) for f in use if f[0].isdigit())
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        reasons = [n for i, n in enumerate(names) if any(f[2 + i].lower().startswith("active") for f in use)]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None,
-                "sm_max_mhz": int(self.samples[0][1]) if self.samples[0][1].isdigit() else None,
-                "reasons": reasons, "samples": len(self.samples)}
+                "sm_max_mhz": int(use[0][1]) if use[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(use), "samples_in_timed_region": len(inside)}
+
+
+def ncu_traffic(kernel, rows):
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/), valid for
+    the 1e8-row workload it was taken on; None otherwise."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        d = json.load(open(p))
+        if d.get("rows") == rows and kernel in d["kernels"]:
+            return d["kernels"][kernel]["dram_bytes_read"] + d["kernels"][kernel]["dram_bytes_write"]
+    except Exception:
+        pass
+    return None
 
 
 def run_reference(args):
@@ -159,6 +192,7 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     barrier()
+    sampler.mark_begin()
     t0 = time.perf_counter()
     dev_ms, phase, launches, result_rows = 0.0, {}, 0, 0
     for _ in range(args.steps):
@@ -171,6 +205,7 @@ def run_ours(args):
         job.release()
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
+    sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
     stats = torch.tensor([dev_ms / args.steps, wall_ms / args.steps], device=dev, dtype=torch.float64)
     if dist is not None:
@@ -213,6 +248,37 @@ def run_ours(args):
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_ms = float(e2e_t[0])
 
+    # ---- e2e, two jobs in flight: a second context (own stream + workspace) on the same GPU, jobs submitted
+    # alternately so that the H2D of job i+1 overlaps the compute and D2H of job i (how the controller's 4
+    # workers drive tad_submit).  Reported separately; `e2e.value` above is one job at a time.
+    pipe_ms = None
+    if world == 1 and not args.no_pipelined:
+        eng2 = TadEngine(device=local)
+        hcols2 = eng2.alloc_columns(rows)
+        for name in cols_t:
+            hcols2.view(name)[:rows] = hcols.view(name)[:rows]
+        hcols2.c.rows = rows
+        engines = [(eng, hcols), (eng2, hcols2)]
+        for e_, c_ in engines:                       # warm both workspaces
+            j_ = e_.submit(c_, algo="EWMA", tad_id="bench")
+            j_.wait(); j_.result(copy=False); j_.release()
+        torch.cuda.synchronize()
+        n_pipe = max(4, args.steps)
+        t0 = time.perf_counter()
+        inflight = []
+        for k in range(n_pipe):
+            e_, c_ = engines[k % 2]
+            if len(inflight) == 2:
+                j_ = inflight.pop(0)
+                j_.wait(); j_.result(copy=False); j_.release()
+            inflight.append(e_.submit(c_, algo="EWMA", tad_id="bench"))
+        for j_ in inflight:
+            j_.wait(); j_.result(copy=False); j_.release()
+        torch.cuda.synchronize()
+        pipe_ms = (time.perf_counter() - t0) * 1e3 / n_pipe
+        hcols2.free()
+        eng2.close()
+
     if rank == 0:
         peak, peak_src = peaks()
         per = {k: v / args.steps for k, v in phase.items()}
@@ -229,10 +295,15 @@ def run_ours(args):
                        "timing": "library CUDA events on its stream; wall clock per step %.3f ms" % ms_wall},
             "e2e": {"value": total_rows / (e2e_ms * 1e-3), "unit": "records/s",
                     "h2d_bytes_per_step": rows * BYTES_PER_ROW, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms, "h2d_ms": h2d_ms},
+                    "ms_per_step": e2e_ms, "h2d_ms": h2d_ms,
+                    "two_jobs_in_flight": None if pipe_ms is None else
+                    {"value": rows / (pipe_ms * 1e-3), "ms_per_step": pipe_ms,
+                     "note": "two contexts on one GPU, H2D of job i+1 overlaps compute + D2H of job i"}},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": ncu_traffic(dom, rows), "peak_source": peak_src,
+                         "note": "achieved = algorithmic bytes (29 B/row; hist 17) / CUDA-event time of the phase; the group phase is "
+                                 "three launches of one kernel template (capacity classes)",
                          "pipeline_frac": rows * BYTES_PER_ROW / (ms_dev * 1e-3) / 1e9 / peak},
             "phase_ms": per, "result_rows": result_rows, "clocks": clocks,
         }
@@ -267,6 +338,7 @@ def main():
     ap.add_argument("--ref-series", type=int, default=100_000, help="connections in the CPU sample")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs: skip the host-buffer leg")
+    ap.add_argument("--no-pipelined", action="store_true", help="skip the two-jobs-in-flight e2e figure")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -85,6 +85,9 @@ enum {
     ST_SERIES,          // total series
     ST_POINTS,          // total points after the reduce
     ST_OUTCOUNT,        // result rows produced (may exceed capacity -> rerun)
+    ST_NCLS0,           // buckets per shared-memory capacity class (1024 / 2048 / 4096 rows)
+    ST_NCLS1,
+    ST_NCLS2,
     ST_COUNT
 };
 

@@ -69,9 +69,10 @@ struct tad_ctx {
     std::thread worker;
     bool stop = false;
     int debug_logb = -1;
+    int debug_target = 0;      // TAD_GROUP_TARGET: mean rows per bucket (tuning)
     int num_sms = 148;
     // device workspace (grow-only, reused across jobs; jobs are serialized by the worker)
-    DevBuf d_col[10], hist, offsets, cursor, big_list, big_base, csr_p, stats, part, csr_v, csr_t, nsb, npb, sbase, outb, ns_ignore, spill,
+    DevBuf d_col[10], hist, offsets, cursor, big_list, big_base, cls_list, csr_p, stats, part, csr_v, csr_t, nsb, npb, sbase, outb, ns_ignore, spill,
         dbx, dbi, exch, scan_sync, small, hist_all, seg_off, seg_total, entries, ar_y, ar_pred, ar_lam;
     unsigned long long *h_small = nullptr;   // pinned, 64 x u64
     uint32_t scan_epoch = 0;
@@ -165,7 +166,8 @@ int pick_logb(const tad_ctx *ctx, uint64_t rows)
 {
     if (ctx->debug_logb >= 0) return ctx->debug_logb;
     // mean bucket ~ 0.375 * capacity: connection sizes are lumpy, so leave head-room
-    const uint64_t target = (uint64_t)kGroupTarget;
+    uint64_t target = (uint64_t)kGroupTarget;
+    if (ctx->debug_target > 0) target = (uint64_t)ctx->debug_target;
     int logb = 0;
     while (logb < 22 && (rows >> logb) > target) logb++;
     return logb;
@@ -349,12 +351,14 @@ void run_job(tad_ctx *ctx, tad_job *job)
     ensure(ctx->cursor, (size_t)B * 4);
     ensure(ctx->big_list, (size_t)B * 4);
     ensure(ctx->big_base, ((size_t)B + 1) * 4);
+    ensure(ctx->cls_list, (size_t)B * 4 * 3);
     ensure(ctx->nsb, (size_t)Bl * 4);
     ensure(ctx->npb, (size_t)Bl * 4);
     ensure(ctx->sbase, ((size_t)Bl + 1) * 4);
     ensure(ctx->part, (R ? R : 1) * sizeof(Row32));
     uint32_t *hist = (uint32_t *)ctx->hist.p, *offsets = (uint32_t *)ctx->offsets.p, *cursor = (uint32_t *)ctx->cursor.p;
     uint32_t *big_base = (uint32_t *)ctx->big_base.p;
+    uint32_t *cls_list = (uint32_t *)ctx->cls_list.p;
     uint32_t *big_list = (uint32_t *)ctx->big_list.p, *nsb = (uint32_t *)ctx->nsb.p, *npb = (uint32_t *)ctx->npb.p;
     uint32_t *sbase = (uint32_t *)ctx->sbase.p;
     Row32 *part = (Row32 *)ctx->part.p;
@@ -389,7 +393,7 @@ void run_job(tad_ctx *ctx, tad_job *job)
     }
     // single GPU: these are the final bucket offsets; multi GPU: offsets inside the local send buffer
     CU(launch_bucket_scan(st, hist, offsets, cursor, B, world > 1 ? 0xffffffffu : (uint32_t)kGroupCap, big_list, big_base,
-                          d_stats, ctx->scan_sync.p, ++ctx->scan_epoch)); launches++;
+                          world > 1 ? nullptr : cls_list, d_stats, ctx->scan_sync.p, ++ctx->scan_epoch)); launches++;
     mark(TAD_PHASE_SCAN);
     CU(launch_scatter(st, c, R, f, logB, cursor, part)); launches += R ? 1 : 0;
     mark(TAD_PHASE_SCATTER);
@@ -442,8 +446,8 @@ void run_job(tad_ctx *ctx, tad_job *job)
             seg.off[p] = seg_off + (size_t)p * (Bl + 1);
         }
         // final (virtual) bucket offsets of the owned range, oversized-bucket list
-        CU(launch_bucket_scan(st, seg_total, offsets, cursor, Bl, kGroupCap, big_list, big_base, d_stats, ctx->scan_sync.p,
-                              ++ctx->scan_epoch)); launches++;
+        CU(launch_bucket_scan(st, seg_total, offsets, cursor, Bl, kGroupCap, big_list, big_base, cls_list, d_stats,
+                              ctx->scan_sync.p, ++ctx->scan_epoch)); launches++;
         mark(TAD_PHASE_EXCHANGE);
         CU(cudaMemcpyAsync(ctx->h_stats, d_stats, ST_COUNT * 4, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
@@ -469,8 +473,8 @@ void run_job(tad_ctx *ctx, tad_job *job)
     mark(-1);
     {
         int l = 0;
-        CU(launch_group(st, seg, entries, offsets, Bl, logB, ctx->h_stats[ST_MAXBUCKET], csr_v, csr_t, csr_p, nsb, npb,
-                        sp.reducer, &l));
+        const uint32_t n_cls[3] = {ctx->h_stats[ST_NCLS0], ctx->h_stats[ST_NCLS1], ctx->h_stats[ST_NCLS2]};
+        CU(launch_group(st, seg, entries, offsets, Bl, logB, cls_list, n_cls, csr_v, csr_t, csr_p, nsb, npb, sp.reducer, &l));
         launches += l;
     }
     mark(TAD_PHASE_GROUP);
@@ -694,6 +698,7 @@ int tad_init(const tad_config *cfg, tad_ctx **out)
     ctx->cfg = *cfg;
     ctx->cfg.nccl_unique_id = nullptr;
     if (const char *e = getenv("TAD_DEBUG_LOGB")) ctx->debug_logb = atoi(e);
+    if (const char *e = getenv("TAD_GROUP_TARGET")) ctx->debug_target = atoi(e);
     cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, cfg->device);
     bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
@@ -729,7 +734,7 @@ void tad_shutdown(tad_ctx *ctx)
     if (ctx->worker.joinable()) ctx->worker.join();
     cudaSetDevice(ctx->cfg.device);
     nccl_comm_destroy(&ctx->nccl);
-    DevBuf *bufs[] = {&ctx->hist, &ctx->offsets, &ctx->cursor, &ctx->big_list, &ctx->big_base, &ctx->csr_p, &ctx->stats, &ctx->part, &ctx->csr_v,
+    DevBuf *bufs[] = {&ctx->hist, &ctx->offsets, &ctx->cursor, &ctx->big_list, &ctx->big_base, &ctx->cls_list, &ctx->csr_p, &ctx->stats, &ctx->part, &ctx->csr_v,
                       &ctx->csr_t, &ctx->nsb, &ctx->npb, &ctx->sbase, &ctx->outb, &ctx->ns_ignore, &ctx->spill, &ctx->dbx,
                       &ctx->dbi, &ctx->exch, &ctx->scan_sync, &ctx->small, &ctx->hist_all, &ctx->seg_off, &ctx->seg_total,
                       &ctx->entries, &ctx->ar_y, &ctx->ar_pred, &ctx->ar_lam};

@@ -4,11 +4,11 @@
 //   bscan    (K1b) exclusive scan of the histogram, oversized-bucket list
 //   scatter  (K2)  columns -> 32 B packed rows, hash-partitioned               reads 29, writes 32 B/row
 //   group    (K3)  one CTA per bucket: TMA bulk load into shared memory, hash-group by
-//                  key, rank-sort each series by flowEndSeconds, reduce duplicates,
+//                  key, O(n) bucket-sort of each series by flowEndSeconds, reduce duplicates,
 //                  write per-series arrays + series entries                   reads 32, writes 12 B/row
 //   sscan    (K3b) exclusive scan of series-per-bucket
-//   detect   (K4)  one thread per series: stddev_samp (Welford, sequential FP64),
-//                  EWMA / DBSCAN score + flag, two-pass anomaly compaction    reads 8-12 B/row
+//   detect   (K4)  one thread per series out of a TMA-staged span: stddev_samp (Welford,
+//                  sequential FP64), EWMA / DBSCAN score + flag, queued emission  reads 8-12 B/row
 //
 // All FP64 arithmetic on the score path uses explicit round-to-nearest intrinsics in the
 // exact operation order of the reference UDFs (anomaly_detection.py:146-212) so that the
@@ -264,6 +264,7 @@ __device__ __forceinline__ void grid_prefix(ScanSync *sy, uint32_t epoch, const 
 __global__ void __launch_bounds__(1024) bucket_scan_kernel(const uint32_t *__restrict__ hist, uint32_t *__restrict__ offsets,
                                                            uint32_t *__restrict__ cursor, uint32_t B, uint32_t cap,
                                                            uint32_t *__restrict__ big_list, uint32_t *__restrict__ big_base,
+                                                           uint32_t *__restrict__ cls_list /* 3 x B, may be null */,
                                                            uint32_t *__restrict__ stats, ScanSync *sy, uint32_t epoch)
 {
     __shared__ uint32_t total_s, nbig_s, bigrows_s, maxb_s;
@@ -297,6 +298,19 @@ __global__ void __launch_bounds__(1024) bucket_scan_kernel(const uint32_t *__res
             big_base[k] = br;
             k++;
             br += h;
+        }
+        if (cls_list) {
+            // bucket list of its shared-memory capacity class (order is irrelevant: one CTA per entry);
+            // one atomic per (warp, class) instead of one per bucket
+            const uint32_t c = (h == 0 || h > cap) ? 3u : (h <= (uint32_t)kGroupCapSmall ? 0u : (h <= (uint32_t)kGroupCapMid ? 1u : 2u));
+            const unsigned peers = __match_any_sync(__activemask(), c);
+            if (c < 3u) {
+                const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+                uint32_t base = 0;
+                if (lane == leader) base = atomicAdd(&stats[ST_NCLS0 + c], (uint32_t)__popc(peers));
+                base = __shfl_sync(peers, base, leader);
+                cls_list[(size_t)c * B + base + __popc(peers & ((1u << lane) - 1u))] = i;
+            }
         }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -419,7 +433,8 @@ __device__ __forceinline__ uint32_t count_lt_u64(const unsigned long long *a, ui
 
 template <int CAP, int NT, bool VRANK>
 __global__ void __launch_bounds__(NT) group_kernel(const SegDesc seg, SeriesEntry *__restrict__ entries,
-                                                   const uint32_t *__restrict__ offsets, uint32_t lo_rows, int sshift,
+                                                   const uint32_t *__restrict__ offsets, const uint32_t *__restrict__ bucket_list,
+                                                   uint32_t lo_rows, int sshift,
                                                    uint64_t *__restrict__ csr_v, uint32_t *__restrict__ csr_t,
                                                    uint32_t *__restrict__ csr_p, uint32_t *__restrict__ nsb,
                                                    uint32_t *__restrict__ npb, int reducer)
@@ -431,7 +446,7 @@ __global__ void __launch_bounds__(NT) group_kernel(const SegDesc seg, SeriesEntr
     extern __shared__ __align__(128) unsigned char smem_raw[];
     S &s = *reinterpret_cast<S *>(smem_raw);
 
-    const uint32_t bkt = blockIdx.x;
+    const uint32_t bkt = bucket_list ? bucket_list[blockIdx.x] : blockIdx.x;
     const uint32_t off_b = offsets[bkt];
     const uint32_t n = offsets[bkt + 1] - off_b;
     const int tid = threadIdx.x;
@@ -773,17 +788,6 @@ __global__ void rcp_table_kernel()
     if (k <= kRcpTable) g_rcp[k] = k ? __drcp_rn((double)k) : 0.0;
 }
 
-__device__ __forceinline__ double div_by_count(double d, double cnt, uint32_t k)
-{
-    if (k <= kRcpTable) {
-        const double r = g_rcp[k];
-        const double q0 = __dmul_rn(d, r);
-        const double q1 = __fma_rn(__fma_rn(-cnt, q0, d), r, q0);
-        return __fma_rn(__fma_rn(-cnt, q1, d), r, q1);
-    }
-    return __ddiv_rn(d, cnt);
-}
-
 // stddev_samp as Spark's CentralMomentAgg computes it (Welford), sequential in time order.  The reciprocals
 // of the next four counts are fetched before the dependent chain of the current four values starts, so the
 // table load never sits on the critical path.
@@ -1123,19 +1127,19 @@ static uint32_t scan_grid(uint32_t B)
 }
 
 cudaError_t launch_bucket_scan(cudaStream_t st, const uint32_t *hist, uint32_t *offsets, uint32_t *cursor, uint32_t B,
-                               uint32_t cap, uint32_t *big_list, uint32_t *big_base, uint32_t *stats, void *scan_sync,
-                               uint32_t epoch)
+                               uint32_t cap, uint32_t *big_list, uint32_t *big_base, uint32_t *cls_list, uint32_t *stats,
+                               void *scan_sync, uint32_t epoch)
 {
-    bucket_scan_kernel<<<scan_grid(B), 1024, 0, st>>>(hist, offsets, cursor, B, cap, big_list, big_base, stats,
+    bucket_scan_kernel<<<scan_grid(B), 1024, 0, st>>>(hist, offsets, cursor, B, cap, big_list, big_base, cls_list, stats,
                                                      static_cast<ScanSync *>(scan_sync), epoch);
     return cudaGetLastError();
 }
 
 template <int CAP, int NT, bool VRANK>
 static cudaError_t launch_group_class(cudaStream_t st, const SegDesc &seg, SeriesEntry *entries, const uint32_t *offsets,
-                                      uint32_t B, uint32_t lo_rows,
-                                      int sshift, uint64_t *csr_v, uint32_t *csr_t, uint32_t *csr_p, uint32_t *nsb,
-                                      uint32_t *npb, int reducer)
+                                      const uint32_t *bucket_list, uint32_t n_buckets, uint32_t lo_rows, int sshift,
+                                      uint64_t *csr_v, uint32_t *csr_t, uint32_t *csr_p, uint32_t *nsb, uint32_t *npb,
+                                      int reducer)
 {
     using S = GroupSmem<CAP, NT>;
     static bool configured = false;
@@ -1145,43 +1149,55 @@ static cudaError_t launch_group_class(cudaStream_t st, const SegDesc &seg, Serie
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    kern<<<B, NT, sizeof(S), st>>>(seg, entries, offsets, lo_rows, sshift, csr_v, csr_t, csr_p, nsb, npb, reducer);
+    if (n_buckets == 0) return cudaSuccess;
+    kern<<<n_buckets, NT, sizeof(S), st>>>(seg, entries, offsets, bucket_list, lo_rows, sshift, csr_v, csr_t, csr_p, nsb, npb,
+                                           reducer);
     return cudaGetLastError();
 }
 
-// Three shared-memory capacity classes (1024 / 2048 / 4096 rows): most buckets fit the first and run at
-// the highest occupancy; `max_bucket` (known on the host after the bucket scan) lets the launcher skip
-// classes no bucket needs.  Empty buckets keep the zeroes the caller memset into nsb / npb.
+// Three shared-memory capacity classes (1024 / 2048 / 4096 rows): most buckets fit the first and run at the
+// highest occupancy.  Each class is launched over ITS OWN bucket list (built by the bucket scan), one CTA per
+// listed bucket -- launching all B CTAs per class and exiting early costs ~0.5 ms per class at 180 KB of shared
+// memory per CTA.  Empty buckets keep the zeroes the caller memset into nsb / npb.
 template <bool VRANK>
 static cudaError_t launch_group_all(cudaStream_t st, const SegDesc &seg, SeriesEntry *entries, const uint32_t *offsets,
-                                    uint32_t B, int sshift, uint32_t max_bucket, uint64_t *csr_v, uint32_t *csr_t,
-                                    uint32_t *csr_p, uint32_t *nsb, uint32_t *npb, int reducer, int *launches)
+                                    uint32_t B, int sshift, const uint32_t *cls_list, const uint32_t n_cls[3], uint64_t *csr_v,
+                                    uint32_t *csr_t, uint32_t *csr_p, uint32_t *nsb, uint32_t *npb, int reducer, int *launches)
 {
-    cudaError_t e = launch_group_class<kGroupCapSmall, 256, VRANK>(st, seg, entries, offsets, B, 0, sshift, csr_v, csr_t, csr_p,
-                                                                   nsb, npb, reducer);
-    *launches = 1;
-    if (e == cudaSuccess && max_bucket > (uint32_t)kGroupCapSmall) {
-        e = launch_group_class<kGroupCapMid, 256, VRANK>(st, seg, entries, offsets, B, kGroupCapSmall, sshift, csr_v, csr_t,
-                                                         csr_p, nsb, npb, reducer);
+    static int small_nt = 0;
+    if (!small_nt) {
+        const char *ev = getenv("TAD_GROUP_NT");          // tuning knob: threads per CTA of the first capacity class
+        small_nt = ev ? atoi(ev) : 256;
+    }
+    *launches = 0;
+    cudaError_t e = small_nt == 128
+                        ? launch_group_class<kGroupCapSmall, 128, VRANK>(st, seg, entries, offsets, cls_list, n_cls[0], 0, sshift,
+                                                                         csr_v, csr_t, csr_p, nsb, npb, reducer)
+                        : launch_group_class<kGroupCapSmall, 256, VRANK>(st, seg, entries, offsets, cls_list, n_cls[0], 0, sshift,
+                                                                         csr_v, csr_t, csr_p, nsb, npb, reducer);
+    *launches += n_cls[0] ? 1 : 0;
+    if (e == cudaSuccess && n_cls[1]) {
+        e = launch_group_class<kGroupCapMid, 256, VRANK>(st, seg, entries, offsets, cls_list + B, n_cls[1], kGroupCapSmall, sshift,
+                                                         csr_v, csr_t, csr_p, nsb, npb, reducer);
         ++*launches;
     }
-    if (e == cudaSuccess && max_bucket > (uint32_t)kGroupCapMid) {
-        e = launch_group_class<kGroupCap, 512, VRANK>(st, seg, entries, offsets, B, kGroupCapMid, sshift, csr_v, csr_t, csr_p,
-                                                      nsb, npb, reducer);
+    if (e == cudaSuccess && n_cls[2]) {
+        e = launch_group_class<kGroupCap, 512, VRANK>(st, seg, entries, offsets, cls_list + 2 * (size_t)B, n_cls[2], kGroupCapMid,
+                                                      sshift, csr_v, csr_t, csr_p, nsb, npb, reducer);
         ++*launches;
     }
     return e;
 }
 
 cudaError_t launch_group(cudaStream_t st, const SegDesc &seg, SeriesEntry *entries, const uint32_t *offsets, uint32_t B,
-                         int logB, uint32_t max_bucket, uint64_t *csr_v, uint32_t *csr_t, uint32_t *csr_p, uint32_t *nsb,
-                         uint32_t *npb, int reducer, int *launches)
+                         int logB, const uint32_t *cls_list, const uint32_t n_cls[3], uint64_t *csr_v, uint32_t *csr_t,
+                         uint32_t *csr_p, uint32_t *nsb, uint32_t *npb, int reducer, int *launches)
 {
     int sshift = 64 - logB - 13;          // 13 hash bits below the bucket bits pick the slot
     if (sshift < 0) sshift = 0;
-    return csr_p ? launch_group_all<true>(st, seg, entries, offsets, B, sshift, max_bucket, csr_v, csr_t, csr_p, nsb, npb,
+    return csr_p ? launch_group_all<true>(st, seg, entries, offsets, B, sshift, cls_list, n_cls, csr_v, csr_t, csr_p, nsb, npb,
                                           reducer, launches)
-                 : launch_group_all<false>(st, seg, entries, offsets, B, sshift, max_bucket, csr_v, csr_t, csr_p, nsb, npb,
+                 : launch_group_all<false>(st, seg, entries, offsets, B, sshift, cls_list, n_cls, csr_v, csr_t, csr_p, nsb, npb,
                                            reducer, launches);
 }
 

@@ -8,16 +8,16 @@ cudaError_t launch_hist(cudaStream_t st, const ColPtrs &c, uint64_t R, const Row
 cudaError_t launch_scatter(cudaStream_t st, const ColPtrs &c, uint64_t R, const RowFilter &f, int logB, uint32_t *cursor,
                            Row32 *part);
 cudaError_t launch_bucket_scan(cudaStream_t st, const uint32_t *hist, uint32_t *offsets, uint32_t *cursor, uint32_t B,
-                               uint32_t cap, uint32_t *big_list, uint32_t *big_base, uint32_t *stats, void *scan_sync,
-                               uint32_t epoch);
+                               uint32_t cap, uint32_t *big_list, uint32_t *big_base, uint32_t *cls_list /* 3 x B or null */,
+                               uint32_t *stats, void *scan_sync, uint32_t epoch);
 size_t scan_sync_bytes();   // zero-initialised once; epoch must be > 0 and differ between launches
 // csr_p != nullptr: also rank every series by value and write the permutation (value rank -> time
 // index) the DBSCAN detector sweeps over.
 // `offsets` are the (virtual, contiguous) bucket offsets used for entries / csr arrays; the rows
 // themselves are read through `seg`.
 cudaError_t launch_group(cudaStream_t st, const SegDesc &seg, SeriesEntry *entries, const uint32_t *offsets, uint32_t B,
-                         int logB, uint32_t max_bucket, uint64_t *csr_v, uint32_t *csr_t, uint32_t *csr_p, uint32_t *nsb,
-                         uint32_t *npb, int reducer, int *launches);
+                         int logB, const uint32_t *cls_list, const uint32_t n_cls[3], uint64_t *csr_v, uint32_t *csr_t,
+                         uint32_t *csr_p, uint32_t *nsb, uint32_t *npb, int reducer, int *launches);
 cudaError_t launch_series_scan(cudaStream_t st, const uint32_t *nsb, const uint32_t *npb, uint32_t *sbase, uint32_t B,
                                uint32_t *stats, void *scan_sync, uint32_t epoch);
 cudaError_t launch_detect_ewma(cudaStream_t st, const SeriesEntry *entries, const uint32_t *offsets, const uint32_t *sbase, uint32_t B,
