@@ -164,6 +164,9 @@ def run_ours(args):
         dist.broadcast_object_list(buf, src=0)
         uid = buf[0]
     eng = TadEngine(device=local, world_size=world, rank=rank, nccl_unique_id=uid)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()              # early: nvidia-smi takes a second or more to enumerate the GPUs
 
     S, n = args.series, args.points
     cols_t = synth.make_flows_torch(S, n, seed=1 + rank, device=dev) if world == 1 else \
@@ -188,9 +191,6 @@ def run_ours(args):
     for _ in range(args.warmup):
         job, st = step(dcols)
         job.release()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     barrier()
     sampler.mark_begin()
     t0 = time.perf_counter()
@@ -222,6 +222,8 @@ def run_ours(args):
             print(json.dumps({"value": total_rows / (ms_dev * 1e-3), "ms_per_step": ms_dev,
                               "phase_ms": {k: v / args.steps for k, v in phase.items()}, "note": "profiling run"}))
         eng.close()
+        if dist is not None:
+            dist.destroy_process_group()
         return
     hcols = eng.alloc_columns(rows)
     for name, tns in cols_t.items():

@@ -38,6 +38,7 @@ def main():
     assert (own[order][1:][same] == own[order][:-1][same]).all()
     if mode == "gpu":
         from theia_b200.engine import TadEngine
+        os.environ["TAD_EXCHANGE_MIN_ROWS"] = "0"        # exercise the chunked (overlapped) exchange on this small table
         uid = [TadEngine.get_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         local = int(os.environ.get("LOCAL_RANK", rank))

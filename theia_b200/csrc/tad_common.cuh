@@ -49,7 +49,7 @@ struct RowFilter {
 // A bucket's rows may arrive as several segments: one per source rank after the multi-GPU exchange
 // (one segment, the local partition buffer itself, on a single GPU).  Segment r holds the rows of
 // this rank's bucket range in bucket order; off[r] is the exclusive row offset of every bucket in it.
-constexpr int kMaxSeg = 8;
+constexpr int kMaxSeg = 32;          // 8 source ranks x 4 exchange chunks
 struct SegDesc {
     const Row32 *base[kMaxSeg];
     const uint32_t *off[kMaxSeg];

@@ -33,6 +33,8 @@ struct PinnedBlock {
 
 constexpr int kMaxEvents = 24;
 constexpr int kMaxChunks = 16;          // host-resident input is copied and histogrammed in chunks
+constexpr int kMaxRanks = 8;
+constexpr int kMaxXChunks = kMaxSeg / kMaxRanks;   // exchange chunks: scatter of chunk c+1 overlaps the all-to-all of chunk c
 constexpr int kTotalStages = 6;   // ingest, partition, exchange, group, detect, egress
 
 double now_ms()
@@ -63,6 +65,9 @@ struct tad_ctx {
     cudaEvent_t ev[kMaxEvents]{};
     cudaEvent_t chunk_ev[kMaxChunks]{};
     cudaEvent_t start_ev = nullptr;
+    cudaEvent_t x_ev[kMaxXChunks + 1]{};
+    int exchange_chunks = kMaxXChunks;
+    uint64_t exchange_min_rows = 1u << 22;   // below this the exchange is not worth chunking (TAD_EXCHANGE_MIN_ROWS)
     std::mutex mu;
     std::condition_variable cv;
     std::deque<tad_job *> queue;
@@ -74,7 +79,7 @@ struct tad_ctx {
     // device workspace (grow-only, reused across jobs; jobs are serialized by the worker)
     DevBuf d_col[10], hist, offsets, cursor, big_list, big_base, cls_list, csr_p, stats, part, csr_v, csr_t, nsb, npb, sbase, outb, ns_ignore, spill,
         dbx, dbi, exch, scan_sync, small, hist_all, seg_off, seg_total, entries, ar_y, ar_pred, ar_lam;
-    unsigned long long *h_small = nullptr;   // pinned, 64 x u64
+    unsigned long long *h_small = nullptr;   // pinned, 256 x u64
     uint32_t scan_epoch = 0;
     uint32_t *h_stats = nullptr;   // pinned readback of the device scalars
     std::mutex pool_mu;
@@ -363,16 +368,75 @@ void run_job(tad_ctx *ctx, tad_job *job)
     uint32_t *sbase = (uint32_t *)ctx->sbase.p;
     Row32 *part = (Row32 *)ctx->part.p;
 
-    CU(cudaMemsetAsync(hist, 0, (size_t)B * 4, st));
     CU(cudaMemsetAsync(nsb, 0, (size_t)Bl * 4, st));
     CU(cudaMemsetAsync(npb, 0, (size_t)Bl * 4, st));
-    mark(-1);
-    if (host_input) {
-        for (int k = 0; k < nchunks; k++) {
-            uint64_t lo, hi;
-            chunk_range(k, lo, hi);
-            CU(cudaStreamWaitEvent(st, ctx->chunk_ev[k], 0));
-            if (hi <= lo) continue;
+    SegDesc seg{};
+    SeriesEntry *entries = nullptr;
+    uint64_t kept = 0, owned = 0;
+    if (world == 1) {
+        CU(cudaMemsetAsync(hist, 0, (size_t)B * 4, st));
+        mark(-1);
+        if (host_input) {
+            for (int k = 0; k < nchunks; k++) {
+                uint64_t lo, hi;
+                chunk_range(k, lo, hi);
+                CU(cudaStreamWaitEvent(st, ctx->chunk_ev[k], 0));
+                if (hi <= lo) continue;
+                ColPtrs ck = c;
+                if (ck.src_ip) ck.src_ip += lo;
+                if (ck.dst_ip) ck.dst_ip += lo;
+                if (ck.src_port) ck.src_port += lo;
+                if (ck.dst_port) ck.dst_port += lo;
+                if (ck.proto) ck.proto += lo;
+                if (ck.flow_start) ck.flow_start += lo;
+                if (ck.flow_end) ck.flow_end += lo;
+                if (ck.value) ck.value += lo;
+                if (ck.src_ns) ck.src_ns += lo;
+                if (ck.dst_ns) ck.dst_ns += lo;
+                CU(launch_hist(st, ck, hi - lo, f, logB, hist)); launches++;
+            }
+            mark(TAD_PHASE_H2D);          // copy + overlapped histogram of all chunks
+        } else {
+            CU(launch_hist(st, c, R, f, logB, hist)); launches += R ? 1 : 0;
+            mark(TAD_PHASE_HIST);
+        }
+        // single GPU: these are the final bucket offsets; multi GPU: offsets inside the local send buffer
+        CU(launch_bucket_scan(st, hist, offsets, cursor, B, world > 1 ? 0xffffffffu : (uint32_t)kGroupCap, big_list, big_base,
+                              world > 1 ? nullptr : cls_list, d_stats, ctx->scan_sync.p, ++ctx->scan_epoch)); launches++;
+        mark(TAD_PHASE_SCAN);
+        CU(launch_scatter(st, c, R, f, logB, cursor, part)); launches += R ? 1 : 0;
+        mark(TAD_PHASE_SCATTER);
+        CU(cudaMemcpyAsync(ctx->h_stats, d_stats, ST_COUNT * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        kept = owned = ctx->h_stats[ST_KEPT];
+        seg.nseg = 1;
+        seg.base[0] = part;
+        seg.off[0] = offsets;
+        entries = reinterpret_cast<SeriesEntry *>(part);      // in place over the staged bucket rows
+    } else {
+        // ---- multi GPU: K row chunks; chunk c is sent over NVLink (comm stream) while chunk c+1 is scattered ------
+        const int K = R >= ctx->exchange_min_rows ? ctx->exchange_chunks : 1;
+        auto xlo = [&](int cidx) -> uint64_t {
+            if (cidx <= 0) return 0;
+            if (cidx >= K) return R;
+            const uint64_t v = ((R * (uint64_t)cidx / K) + 15) & ~uint64_t(15);
+            return v < R ? v : R;
+        };
+        const int NS = world * K;                              // segments: (source rank, chunk)
+        ensure(ctx->hist, (size_t)B * 4 * K);
+        ensure(ctx->offsets, ((size_t)B + 1) * 4 * K);
+        ensure(ctx->cursor, (size_t)B * 4 * K);
+        ensure(ctx->hist_all, (size_t)B * 4 * NS);
+        ensure(ctx->seg_off, ((size_t)Bl + 1) * 4 * NS);
+        ensure(ctx->seg_total, (size_t)Bl * 4);
+        hist = (uint32_t *)ctx->hist.p; offsets = (uint32_t *)ctx->offsets.p; cursor = (uint32_t *)ctx->cursor.p;
+        uint32_t *hist_all = (uint32_t *)ctx->hist_all.p, *seg_off = (uint32_t *)ctx->seg_off.p;
+        uint32_t *seg_total = (uint32_t *)ctx->seg_total.p;
+        CU(cudaMemsetAsync(hist, 0, (size_t)B * 4 * K, st));
+        if (host_input)
+            for (int k = 0; k < nchunks; k++) CU(cudaStreamWaitEvent(st, ctx->chunk_ev[k], 0));
+        mark(TAD_PHASE_H2D);
+        auto chunk_cols = [&](uint64_t lo) {
             ColPtrs ck = c;
             if (ck.src_ip) ck.src_ip += lo;
             if (ck.dst_ip) ck.dst_ip += lo;
@@ -384,71 +448,68 @@ void run_job(tad_ctx *ctx, tad_job *job)
             if (ck.value) ck.value += lo;
             if (ck.src_ns) ck.src_ns += lo;
             if (ck.dst_ns) ck.dst_ns += lo;
-            CU(launch_hist(st, ck, hi - lo, f, logB, hist)); launches++;
+            return ck;
+        };
+        for (int cx = 0; cx < K; cx++) {
+            const uint64_t lo = xlo(cx), hi = xlo(cx + 1);
+            if (hi > lo) { CU(launch_hist(st, chunk_cols(lo), hi - lo, f, logB, hist + (size_t)cx * B)); launches++; }
         }
-        mark(TAD_PHASE_H2D);          // copy + overlapped histogram of all chunks
-    } else {
-        CU(launch_hist(st, c, R, f, logB, hist)); launches += R ? 1 : 0;
         mark(TAD_PHASE_HIST);
-    }
-    // single GPU: these are the final bucket offsets; multi GPU: offsets inside the local send buffer
-    CU(launch_bucket_scan(st, hist, offsets, cursor, B, world > 1 ? 0xffffffffu : (uint32_t)kGroupCap, big_list, big_base,
-                          world > 1 ? nullptr : cls_list, d_stats, ctx->scan_sync.p, ++ctx->scan_epoch)); launches++;
-    mark(TAD_PHASE_SCAN);
-    CU(launch_scatter(st, c, R, f, logB, cursor, part)); launches += R ? 1 : 0;
-    mark(TAD_PHASE_SCATTER);
-
-    SegDesc seg{};
-    SeriesEntry *entries = nullptr;
-    uint64_t kept = 0, owned = 0;
-    if (world == 1) {
-        CU(cudaMemcpyAsync(ctx->h_stats, d_stats, ST_COUNT * 4, cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
-        kept = owned = ctx->h_stats[ST_KEPT];
-        seg.nseg = 1;
-        seg.base[0] = part;
-        seg.off[0] = offsets;
-        entries = reinterpret_cast<SeriesEntry *>(part);      // in place over the staged bucket rows
-    } else {
-        // ---- exchange: one all-gather of the histograms + one all-to-all-v of packed rows -----------
-        mark(-1);
-        ensure(ctx->hist_all, (size_t)B * 4 * world);
-        ensure(ctx->seg_off, ((size_t)Bl + 1) * 4 * world);
-        ensure(ctx->seg_total, (size_t)Bl * 4);
-        uint32_t *hist_all = (uint32_t *)ctx->hist_all.p, *seg_off = (uint32_t *)ctx->seg_off.p;
-        uint32_t *seg_total = (uint32_t *)ctx->seg_total.p;
-        if (nccl_allgather(&ctx->nccl, hist, hist_all, (size_t)B * 4, st)) fail(TAD_ERR_NCCL, "%s", nccl_last_error());
-        CU(launch_segment_scan(st, hist_all, B, b_lo, Bl, world, seg_off, seg_total, d_small)); launches += 2;
-        // rows this rank sends to rank p = offsets[(p+1)*Bl] - offsets[p*Bl]
-        CU(cudaMemcpy2DAsync(ctx->h_small + 16, 8, offsets, (size_t)Bl * 4, 4, world + 1, cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(ctx->h_small, d_small, 8 * world, cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(ctx->h_stats, d_stats, ST_COUNT * 4, cudaMemcpyDeviceToHost, st));
+        for (int cx = 0; cx < K; cx++) {
+            CU(launch_bucket_scan(st, hist + (size_t)cx * B, offsets + (size_t)cx * (B + 1), cursor + (size_t)cx * B, B, 0xffffffffu,
+                                  big_list, big_base, nullptr, d_stats, ctx->scan_sync.p, ++ctx->scan_epoch)); launches++;
+        }
+        mark(TAD_PHASE_SCAN);
+        // every rank learns every (rank, chunk) histogram: segment offsets of the owned bucket range, receive sizes
+        if (nccl_allgather(&ctx->nccl, hist, hist_all, (size_t)B * 4 * K, st)) fail(TAD_ERR_NCCL, "%s", nccl_last_error());
+        CU(launch_segment_scan(st, hist_all, B, b_lo, Bl, NS, seg_off, seg_total, d_small)); launches += 2;
+        CU(cudaMemcpyAsync(ctx->h_small, d_small, 8 * NS, cudaMemcpyDeviceToHost, st));
+        for (int cx = 0; cx < K; cx++)        // send boundaries of chunk cx: offsets_cx[p * Bl], p = 0..world
+            CU(cudaMemcpy2DAsync(ctx->h_small + 64 + cx * (kMaxRanks + 1), 8, offsets + (size_t)cx * (B + 1), (size_t)Bl * 4, 4,
+                                 world + 1, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         check_cancel();
-        kept = ctx->h_stats[ST_KEPT];
-        uint64_t send_off[kMaxSeg], send_bytes[kMaxSeg], recv_off[kMaxSeg], recv_bytes[kMaxSeg], recv_total = 0;
-        for (int p = 0; p < world; p++) {
-            const uint32_t lo = (uint32_t)ctx->h_small[16 + p], hi = (uint32_t)ctx->h_small[16 + p + 1];
-            send_off[p] = (uint64_t)lo * 32;
-            send_bytes[p] = (uint64_t)(hi - lo) * 32;
-            recv_bytes[p] = ctx->h_small[p] * 32;
-            recv_off[p] = recv_total;
-            if (p != me) recv_total += recv_bytes[p];
-            owned += ctx->h_small[p];
+        uint64_t recv_off[kMaxSeg], recv_total = 0, send_lo[kMaxXChunks][kMaxRanks + 1];
+        for (int sgi = 0; sgi < NS; sgi++) {
+            recv_off[sgi] = recv_total;
+            if (sgi / K != me) recv_total += ctx->h_small[sgi] * 32;
+            owned += ctx->h_small[sgi];
+        }
+        for (int cx = 0; cx < K; cx++) {
+            for (int p = 0; p <= world; p++) send_lo[cx][p] = (uint32_t)ctx->h_small[64 + cx * (kMaxRanks + 1) + p];
+            kept += send_lo[cx][world];
         }
         if (owned >= (1ull << 32) - 1) fail(TAD_ERR_INVALID_ARG, "more than 2^32-2 rows owned by one GPU after the exchange");
         ensure(ctx->exch, recv_total ? recv_total : 32);
-        if (nccl_alltoallv(&ctx->nccl, part, send_off, send_bytes, ctx->exch.p, recv_off, recv_bytes, st))
-            fail(TAD_ERR_NCCL, "%s", nccl_last_error());
-        seg.nseg = world;
-        for (int p = 0; p < world; p++) {
-            seg.base[p] = p == me ? part + (send_off[me] / 32) : reinterpret_cast<const Row32 *>((const char *)ctx->exch.p + recv_off[p]);
-            seg.off[p] = seg_off + (size_t)p * (Bl + 1);
+        cudaStream_t cs = ctx->copy_stream;
+        for (int cx = 0; cx < K; cx++) {
+            const uint64_t lo = xlo(cx), hi = xlo(cx + 1);
+            if (hi > lo) { CU(launch_scatter(st, chunk_cols(lo), hi - lo, f, logB, cursor + (size_t)cx * B, part + lo)); launches++; }
+            CU(cudaEventRecord(ctx->x_ev[cx], st));
+            CU(cudaStreamWaitEvent(cs, ctx->x_ev[cx], 0));
+            uint64_t so[kMaxRanks], sb[kMaxRanks], ro[kMaxRanks], rb[kMaxRanks];
+            for (int p = 0; p < world; p++) {
+                so[p] = (lo + send_lo[cx][p]) * 32;
+                sb[p] = (send_lo[cx][p + 1] - send_lo[cx][p]) * 32;
+                ro[p] = recv_off[p * K + cx];
+                rb[p] = ctx->h_small[p * K + cx] * 32;
+            }
+            if (nccl_alltoallv(&ctx->nccl, part, so, sb, ctx->exch.p, ro, rb, cs)) fail(TAD_ERR_NCCL, "%s", nccl_last_error());
         }
-        // final (virtual) bucket offsets of the owned range, oversized-bucket list
+        mark(TAD_PHASE_SCATTER);
+        CU(cudaEventRecord(ctx->x_ev[K], cs));
+        CU(cudaStreamWaitEvent(st, ctx->x_ev[K], 0));
+        seg.nseg = NS;
+        for (int sgi = 0; sgi < NS; sgi++) {
+            const int r = sgi / K, cx = sgi % K;
+            seg.base[sgi] = r == me ? part + xlo(cx) + send_lo[cx][me]
+                                    : reinterpret_cast<const Row32 *>((const char *)ctx->exch.p + recv_off[sgi]);
+            seg.off[sgi] = seg_off + (size_t)sgi * (Bl + 1);
+        }
+        // final (virtual) bucket offsets of the owned range, oversized-bucket list, capacity-class lists
         CU(launch_bucket_scan(st, seg_total, offsets, cursor, Bl, kGroupCap, big_list, big_base, cls_list, d_stats,
                               ctx->scan_sync.p, ++ctx->scan_epoch)); launches++;
-        mark(TAD_PHASE_EXCHANGE);
+        mark(TAD_PHASE_EXCHANGE);           // = the part of the exchange NOT hidden behind the scatter
         CU(cudaMemcpyAsync(ctx->h_stats, d_stats, ST_COUNT * 4, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         ensure(ctx->entries, (owned ? owned : 1) * sizeof(SeriesEntry));
@@ -685,7 +746,7 @@ int tad_init(const tad_config *cfg, tad_ctx **out)
 {
     if (!cfg || !out) return TAD_ERR_INVALID_ARG;
     if (cfg->world_size < 1 || cfg->rank < 0 || cfg->rank >= cfg->world_size) return TAD_ERR_INVALID_ARG;
-    if (cfg->world_size > kMaxSeg || (cfg->world_size & (cfg->world_size - 1))) return TAD_ERR_INVALID_ARG;   // 1, 2, 4, 8
+    if (cfg->world_size > kMaxRanks || (cfg->world_size & (cfg->world_size - 1))) return TAD_ERR_INVALID_ARG;   // 1, 2, 4, 8
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         cudaGetLastError();
@@ -704,9 +765,12 @@ int tad_init(const tad_config *cfg, tad_ctx **out)
     ok = ok && cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
     for (int i = 0; ok && i < kMaxChunks; i++) ok = cudaEventCreateWithFlags(&ctx->chunk_ev[i], cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&ctx->start_ev, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; ok && i <= kMaxXChunks; i++) ok = cudaEventCreateWithFlags(&ctx->x_ev[i], cudaEventDisableTiming) == cudaSuccess;
+    if (const char *e = getenv("TAD_EXCHANGE_MIN_ROWS")) ctx->exchange_min_rows = strtoull(e, nullptr, 10);
+    if (const char *e = getenv("TAD_EXCHANGE_CHUNKS")) ctx->exchange_chunks = atoi(e) < 1 ? 1 : (atoi(e) > kMaxXChunks ? kMaxXChunks : atoi(e));
     for (int i = 0; ok && i < kMaxEvents; i++) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
     ok = ok && cudaHostAlloc((void **)&ctx->h_stats, 64 * sizeof(uint32_t), cudaHostAllocDefault) == cudaSuccess;
-    ok = ok && cudaHostAlloc((void **)&ctx->h_small, 64 * sizeof(unsigned long long), cudaHostAllocDefault) == cudaSuccess;
+    ok = ok && cudaHostAlloc((void **)&ctx->h_small, 256 * sizeof(unsigned long long), cudaHostAllocDefault) == cudaSuccess;
     if (!ok) {
         delete ctx;
         return TAD_ERR_CUDA;
@@ -750,6 +814,8 @@ void tad_shutdown(tad_ctx *ctx)
     for (int i = 0; i < kMaxChunks; i++)
         if (ctx->chunk_ev[i]) cudaEventDestroy(ctx->chunk_ev[i]);
     if (ctx->start_ev) cudaEventDestroy(ctx->start_ev);
+    for (int i = 0; i <= kMaxXChunks; i++)
+        if (ctx->x_ev[i]) cudaEventDestroy(ctx->x_ev[i]);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
