@@ -10,6 +10,9 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # the ARIMA oracle evaluates likelihoods at degenerate parameters (overflow -> -1e300 by design)
+    config.addinivalue_line("filterwarnings", "ignore::RuntimeWarning")
+    config.addinivalue_line("filterwarnings", "ignore::UserWarning:scipy")
 
 
 @pytest.fixture(scope="session")

@@ -843,8 +843,9 @@ constexpr int kDetectThreads = 96;
 constexpr int kDetectStage = 10240;                   // staged u64 values per CTA
 constexpr int kDetectQueue = 1024;                    // queued result rows per CTA
 
+template <bool STAGED>
 struct DetectSmem {
-    alignas(128) unsigned long long stage[kDetectStage];
+    alignas(128) unsigned long long stage[STAGED ? kDetectStage : 2];
     double qcalc[kDetectQueue];
     uint32_t qmeta[kDetectQueue];                     // bit 31: flag, bits 30..16: owning thread, low 16: unused
     uint32_t qpos[kDetectQueue];                      // index of the point in csr_v / csr_t
@@ -856,14 +857,14 @@ struct DetectSmem {
     uint32_t win[kBucketWindow + 1];
 };
 
-template <int NT>
+template <int NT, bool STAGED>
 __global__ void __launch_bounds__(NT) detect_ewma_kernel(const SeriesEntry *__restrict__ entries, const uint32_t *__restrict__ offsets,
                                                          const uint32_t *__restrict__ sbase, uint32_t B, uint32_t S,
                                                          const uint64_t *__restrict__ csr_v, const uint32_t *__restrict__ csr_t,
                                                          OutCols out, uint32_t out_cap, uint32_t *__restrict__ stats, int emit_all)
 {
     extern __shared__ __align__(128) unsigned char detect_smem[];
-    DetectSmem &sm = *reinterpret_cast<DetectSmem *>(detect_smem);
+    DetectSmem<STAGED> &sm = *reinterpret_cast<DetectSmem<STAGED> *>(detect_smem);
     const uint32_t i = blockIdx.x * NT + threadIdx.x;
     if (threadIdx.x == 0) {
         sm.span_lo = 0xffffffffu;
@@ -889,7 +890,7 @@ __global__ void __launch_bounds__(NT) detect_ewma_kernel(const SeriesEntry *__re
     }
     __syncthreads();
     const uint32_t lo_a = sm.span_lo & ~3u;                      // keep the 32-byte sector phase of csr_v
-    const bool staged = sm.span_hi > lo_a && sm.span_hi - lo_a <= (uint32_t)kDetectStage;
+    const bool staged = STAGED && sm.span_hi > lo_a && sm.span_hi - lo_a <= (uint32_t)kDetectStage;
     if (staged) {
         if (threadIdx.x == 0) {
             const uint32_t bytes = ((sm.span_hi - lo_a) * 8u + 15u) & ~15u;
@@ -1213,6 +1214,7 @@ static void ensure_rcp_table(cudaStream_t st)
     static bool done = false;
     if (!done) {
         rcp_table_kernel<<<(kRcpTable + 256) / 256, 256, 0, st>>>();
+        cudaStreamSynchronize(st);      // once per process: other contexts (streams) of this device read the table too
         done = true;
     }
 }
@@ -1223,16 +1225,21 @@ cudaError_t launch_detect_ewma(cudaStream_t st, const SeriesEntry *entries, cons
 {
     if (S == 0) return cudaSuccess;
     constexpr int NT = kDetectThreads;
-    constexpr int smem = (int)sizeof(DetectSmem);
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(detect_ewma_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    static int staged = -1;
+    if (staged < 0) {
+        const char *ev = getenv("TAD_DETECT_STAGED");        // tuning knob: 1 = TMA-staged span (2 CTAs/SM), 0 = global loads at full occupancy
+        staged = ev ? atoi(ev) : 1;
+        cudaError_t e = cudaFuncSetAttribute(detect_ewma_kernel<NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)sizeof(DetectSmem<true>));
         if (e != cudaSuccess) return e;
-        configured = true;
     }
     ensure_rcp_table(st);
-    detect_ewma_kernel<NT><<<(S + NT - 1) / NT, NT, smem, st>>>(entries, offsets, sbase, B, S, csr_v, csr_t, out, out_cap, stats,
-                                                               emit_all);
+    if (staged)
+        detect_ewma_kernel<NT, true><<<(S + NT - 1) / NT, NT, sizeof(DetectSmem<true>), st>>>(entries, offsets, sbase, B, S, csr_v, csr_t,
+                                                                                            out, out_cap, stats, emit_all);
+    else
+        detect_ewma_kernel<NT, false><<<(S + NT - 1) / NT, NT, sizeof(DetectSmem<false>), st>>>(entries, offsets, sbase, B, S, csr_v,
+                                                                                              csr_t, out, out_cap, stats, emit_all);
     return cudaGetLastError();
 }
 
