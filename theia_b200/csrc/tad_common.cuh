@@ -54,6 +54,7 @@ struct SegDesc {
     const Row32 *base[kMaxSeg];
     const uint32_t *off[kMaxSeg];
     int nseg;
+    uint32_t stride;      // != 0 (single segment only): bucket b starts at base[0] + b * stride (fixed-capacity slots)
 };
 
 struct OutCols {
@@ -88,6 +89,7 @@ enum {
     ST_NCLS0,           // buckets per shared-memory capacity class (1024 / 2048 / 4096 rows)
     ST_NCLS1,
     ST_NCLS2,
+    ST_OVF,             // optimistic partition: rows that did not fit their bucket's fixed-capacity slot
     ST_COUNT
 };
 

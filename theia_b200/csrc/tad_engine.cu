@@ -1,6 +1,7 @@
 // Host side of the TAD engine: C ABI (include/theia_tad.h), job queue, workspace, phase
 // orchestration.  One worker thread per context runs jobs FIFO on one CUDA stream; callers
 // (the controller's workers, pkg/controller/util.go:43) only enqueue and poll.
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
@@ -78,7 +79,8 @@ struct tad_ctx {
     int num_sms = 148;
     // device workspace (grow-only, reused across jobs; jobs are serialized by the worker)
     DevBuf d_col[10], hist, offsets, cursor, big_list, big_base, cls_list, csr_p, stats, part, csr_v, csr_t, nsb, npb, sbase, outb, ns_ignore, spill,
-        dbx, dbi, exch, scan_sync, small, hist_all, seg_off, seg_total, entries, ar_y, ar_pred, ar_lam;
+        dbx, dbi, exch, scan_sync, small, hist_all, seg_off, seg_total, entries, ar_y, ar_pred, ar_lam, ovf;
+    int optimistic = 1;      // TAD_OPTIMISTIC=0: always the exact (histogram + scan + scatter) partition
     unsigned long long *h_small = nullptr;   // pinned, 256 x u64
     uint32_t scan_epoch = 0;
     uint32_t *h_stats = nullptr;   // pinned readback of the device scalars
@@ -373,7 +375,73 @@ void run_job(tad_ctx *ctx, tad_job *job)
     SegDesc seg{};
     SeriesEntry *entries = nullptr;
     uint64_t kept = 0, owned = 0;
-    if (world == 1) {
+    bool partitioned = false;
+    uint32_t n_ovf = 0;
+    const Row32 *ovf_rows = nullptr;
+    auto offset_cols = [&](uint64_t lo) {
+        ColPtrs ck = c;
+        if (ck.src_ip) ck.src_ip += lo;
+        if (ck.dst_ip) ck.dst_ip += lo;
+        if (ck.src_port) ck.src_port += lo;
+        if (ck.dst_port) ck.dst_port += lo;
+        if (ck.proto) ck.proto += lo;
+        if (ck.flow_start) ck.flow_start += lo;
+        if (ck.flow_end) ck.flow_end += lo;
+        if (ck.value) ck.value += lo;
+        if (ck.src_ns) ck.src_ns += lo;
+        if (ck.dst_ns) ck.dst_ns += lo;
+        return ck;
+    };
+    // ---- single GPU, optimistic partition: no histogram pass.  Bucket b owns a fixed slot of kGroupCap rows; a
+    // row that finds its slot full goes to the overflow list, and such buckets take the spill path.  With host input
+    // the scatter of H2D chunk i runs while chunk i+1 is on the bus.  Falls back to the exact two-pass partition
+    // when the overflow list fills up (heavily skewed tables).
+    constexpr uint32_t kSlot = kGroupCap;      // = the largest shared-memory class: overflow is as rare as a spill was
+    const uint64_t slot_rows = (uint64_t)B * kSlot;
+    if (world == 1 && ctx->optimistic && R > 0 && slot_rows * sizeof(Row32) <= (64ull << 30)) {
+        const uint64_t ovf_cap = std::max<uint64_t>(1u << 20, R / 32);
+        ensure(ctx->part, slot_rows * sizeof(Row32));
+        ensure(ctx->ovf, ovf_cap * sizeof(Row32));
+        part = (Row32 *)ctx->part.p;
+        Row32 *ovf = (Row32 *)ctx->ovf.p;
+        CU(cudaMemsetAsync(cursor, 0, (size_t)B * 4, st));
+        mark(-1);
+        if (host_input) {
+            for (int k = 0; k < nchunks; k++) {
+                uint64_t lo, hi;
+                chunk_range(k, lo, hi);
+                CU(cudaStreamWaitEvent(st, ctx->chunk_ev[k], 0));
+                if (hi <= lo) continue;
+                CU(launch_scatter(st, offset_cols(lo), hi - lo, f, logB, cursor, part, kSlot, ovf, (uint32_t)ovf_cap,
+                                  d_stats + ST_OVF)); launches++;
+            }
+            mark(TAD_PHASE_H2D);          // copy + overlapped scatter of all chunks
+        } else {
+            CU(launch_scatter(st, c, R, f, logB, cursor, part, kSlot, ovf, (uint32_t)ovf_cap, d_stats + ST_OVF)); launches++;
+            mark(TAD_PHASE_SCATTER);
+        }
+        // arrival counts -> (virtual) bucket offsets, capacity-class lists, list of over-full buckets
+        CU(launch_bucket_scan(st, cursor, offsets, hist /* unused cursor copy */, B, kSlot, big_list, big_base, cls_list,
+                              d_stats, ctx->scan_sync.p, ++ctx->scan_epoch)); launches++;
+        mark(TAD_PHASE_SCAN);
+        CU(cudaMemcpyAsync(ctx->h_stats, d_stats, ST_COUNT * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if (ctx->h_stats[ST_OVF] <= ovf_cap) {
+            partitioned = true;
+            n_ovf = ctx->h_stats[ST_OVF];
+            ovf_rows = ovf;
+            kept = owned = ctx->h_stats[ST_KEPT];
+            seg.nseg = 1;
+            seg.base[0] = part;
+            seg.off[0] = offsets;
+            seg.stride = kSlot;
+            ensure(ctx->entries, (owned ? owned : 1) * sizeof(SeriesEntry));
+            entries = static_cast<SeriesEntry *>(ctx->entries.p);
+        } else {
+            CU(cudaMemsetAsync(d_stats, 0, 64 * sizeof(uint32_t), st));      // discard; redo exactly
+        }
+    }
+    if (world == 1 && !partitioned) {
         CU(cudaMemsetAsync(hist, 0, (size_t)B * 4, st));
         mark(-1);
         if (host_input) {
@@ -413,7 +481,7 @@ void run_job(tad_ctx *ctx, tad_job *job)
         seg.base[0] = part;
         seg.off[0] = offsets;
         entries = reinterpret_cast<SeriesEntry *>(part);      // in place over the staged bucket rows
-    } else {
+    } else if (world > 1) {
         // ---- multi GPU: K row chunks; chunk c is sent over NVLink (comm stream) while chunk c+1 is scattered ------
         const int K = R >= ctx->exchange_min_rows ? ctx->exchange_chunks : 1;
         auto xlo = [&](int cidx) -> uint64_t {
@@ -544,7 +612,7 @@ void run_job(tad_ctx *ctx, tad_job *job)
         ensure(ctx->spill, need);
         int l = 0;
         CU(run_spill(st, seg, entries, offsets, big_list, big_base, n_big, big_rows, ctx->spill.p, ctx->spill.cap, csr_v, csr_t,
-                     nsb, npb, sp.reducer, &l));
+                     nsb, npb, sp.reducer, &l, ovf_rows, n_ovf));
         launches += l;
         mark(TAD_PHASE_SPILL);
     }
@@ -634,7 +702,8 @@ void run_job(tad_ctx *ctx, tad_job *job)
     // device span excludes the H2D/D2H copies: first partition event .. last detect event
     int first_k = -1, last_k = -1;
     for (int i = 0; i < nev; i++) {
-        if ((ev_phase[i] == TAD_PHASE_HIST || ev_phase[i] == TAD_PHASE_H2D) && first_k < 0) first_k = i - 1;
+        if ((ev_phase[i] == TAD_PHASE_HIST || ev_phase[i] == TAD_PHASE_H2D || ev_phase[i] == TAD_PHASE_SCATTER) && first_k < 0)
+            first_k = i - 1;
         if (ev_phase[i] == TAD_PHASE_DETECT) last_k = i;
     }
     if (first_k >= 0 && last_k > first_k) CU(cudaEventElapsedTime(&total, ctx->ev[first_k], ctx->ev[last_k]));
@@ -766,6 +835,7 @@ int tad_init(const tad_config *cfg, tad_ctx **out)
     for (int i = 0; ok && i < kMaxChunks; i++) ok = cudaEventCreateWithFlags(&ctx->chunk_ev[i], cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&ctx->start_ev, cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; ok && i <= kMaxXChunks; i++) ok = cudaEventCreateWithFlags(&ctx->x_ev[i], cudaEventDisableTiming) == cudaSuccess;
+    if (const char *e = getenv("TAD_OPTIMISTIC")) ctx->optimistic = atoi(e);
     if (const char *e = getenv("TAD_EXCHANGE_MIN_ROWS")) ctx->exchange_min_rows = strtoull(e, nullptr, 10);
     if (const char *e = getenv("TAD_EXCHANGE_CHUNKS")) ctx->exchange_chunks = atoi(e) < 1 ? 1 : (atoi(e) > kMaxXChunks ? kMaxXChunks : atoi(e));
     for (int i = 0; ok && i < kMaxEvents; i++) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
@@ -801,7 +871,7 @@ void tad_shutdown(tad_ctx *ctx)
     DevBuf *bufs[] = {&ctx->hist, &ctx->offsets, &ctx->cursor, &ctx->big_list, &ctx->big_base, &ctx->cls_list, &ctx->csr_p, &ctx->stats, &ctx->part, &ctx->csr_v,
                       &ctx->csr_t, &ctx->nsb, &ctx->npb, &ctx->sbase, &ctx->outb, &ctx->ns_ignore, &ctx->spill, &ctx->dbx,
                       &ctx->dbi, &ctx->exch, &ctx->scan_sync, &ctx->small, &ctx->hist_all, &ctx->seg_off, &ctx->seg_total,
-                      &ctx->entries, &ctx->ar_y, &ctx->ar_pred, &ctx->ar_lam};
+                      &ctx->entries, &ctx->ar_y, &ctx->ar_pred, &ctx->ar_lam, &ctx->ovf};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     for (int i = 0; i < 10; i++)

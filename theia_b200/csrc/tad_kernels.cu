@@ -77,16 +77,38 @@ __device__ __forceinline__ bool row_keep(const RowFilter &f, const ColPtrs &c, u
     return keep;
 }
 
+// Optimistic scatter (no histogram pass): every bucket owns a fixed slot of `cap` rows at part + bucket * cap;
+// counters[] count arrivals from zero; a row whose arrival index is >= cap goes to the overflow list instead.
+struct OptScatter {
+    uint32_t cap;            // 0 = exact mode (counters hold absolute cursors)
+    uint32_t ovf_cap;
+    Row32 *ovf;
+    uint32_t *ovf_count;
+};
+
+__device__ __forceinline__ void place_row(const RowRegs &r, uint32_t bucket, uint32_t pos, Row32 *part, const OptScatter &o)
+{
+    const uint4 lo = make_uint4((uint32_t)r.a, (uint32_t)(r.a >> 32), (uint32_t)r.b, (uint32_t)(r.b >> 32));
+    const uint4 hi = make_uint4((uint32_t)r.value, (uint32_t)(r.value >> 32), r.t, r.proto);
+    if (o.cap == 0) {
+        stg256(part + pos, lo, hi);
+    } else if (pos < o.cap) {
+        stg256(part + (size_t)bucket * o.cap + pos, lo, hi);
+    } else {
+        const uint32_t k = atomicAdd(o.ovf_count, 1u);
+        if (k < o.ovf_cap) stg256(o.ovf + k, lo, hi);
+    }
+}
+
+
 template <bool SCATTER>
-__device__ __forceinline__ void emit_row(const RowRegs &r, int bshift, uint32_t *counters, Row32 *part)
+__device__ __forceinline__ void emit_row(const RowRegs &r, int bshift, uint32_t *counters, Row32 *part, const OptScatter &o)
 {
     if (!r.keep) return;
     const uint64_t h = key_hash(r.a, r.b, r.proto);
     const uint32_t bucket = bshift >= 64 ? 0u : (uint32_t)(h >> bshift);
     if (SCATTER) {
-        const uint32_t pos = atomicAdd(&counters[bucket], 1u);
-        stg256(part + pos, make_uint4((uint32_t)r.a, (uint32_t)(r.a >> 32), (uint32_t)r.b, (uint32_t)(r.b >> 32)),
-               make_uint4((uint32_t)r.value, (uint32_t)(r.value >> 32), r.t, r.proto));
+        place_row(r, bucket, atomicAdd(&counters[bucket], 1u), part, o);
     } else {
         atomicAdd(&counters[bucket], 1u);
     }
@@ -109,7 +131,8 @@ __device__ __forceinline__ void load_row_scalar(const ColPtrs &c, const RowFilte
 // 8 rows per thread, every column read with 128-bit (64-bit for the u8 column) streaming loads.
 template <bool SCATTER, bool VEC>
 __global__ void __launch_bounds__(256) partition_kernel(ColPtrs c, uint64_t R, RowFilter f, int bshift,
-                                                        uint32_t *__restrict__ counters, Row32 *__restrict__ part)
+                                                        uint32_t *__restrict__ counters, Row32 *__restrict__ part,
+                                                        const OptScatter opt)
 {
     const uint64_t ngroups = (R + 7) / 8;
     const bool need_end = SCATTER || f.end_time != 0;
@@ -155,30 +178,26 @@ __global__ void __launch_bounds__(256) partition_kernel(ColPtrs c, uint64_t R, R
             }
             if (SCATTER) {
                 // all eight cursor atomics in flight before the first dependent store
-                uint32_t pos[8];
+                uint32_t pos[8], bkt[8];
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
                     const uint64_t h = key_hash(r[i].a, r[i].b, r[i].proto);
-                    const uint32_t bucket = bshift >= 64 ? 0u : (uint32_t)(h >> bshift);
-                    pos[i] = r[i].keep ? atomicAdd(&counters[bucket], 1u) : 0xffffffffu;
+                    bkt[i] = bshift >= 64 ? 0u : (uint32_t)(h >> bshift);
+                    pos[i] = r[i].keep ? atomicAdd(&counters[bkt[i]], 1u) : 0xffffffffu;
                 }
 #pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    if (pos[i] != 0xffffffffu)
-                        stg256(part + pos[i],
-                               make_uint4((uint32_t)r[i].a, (uint32_t)(r[i].a >> 32), (uint32_t)r[i].b, (uint32_t)(r[i].b >> 32)),
-                               make_uint4((uint32_t)r[i].value, (uint32_t)(r[i].value >> 32), r[i].t, r[i].proto));
-                }
+                for (int i = 0; i < 8; i++)
+                    if (r[i].keep) place_row(r[i], bkt[i], pos[i], part, opt);
             } else {
 #pragma unroll
-                for (int i = 0; i < 8; i++) emit_row<SCATTER>(r[i], bshift, counters, part);
+                for (int i = 0; i < 8; i++) emit_row<SCATTER>(r[i], bshift, counters, part, opt);
             }
         } else {
             const uint64_t end = base + 8 < R ? base + 8 : R;
             for (uint64_t i = base; i < end; i++) {
                 RowRegs r;
                 load_row_scalar(c, f, i, SCATTER, r);
-                emit_row<SCATTER>(r, bshift, counters, part);
+                emit_row<SCATTER>(r, bshift, counters, part, opt);
             }
         }
     }
@@ -464,7 +483,8 @@ __global__ void __launch_bounds__(NT) group_kernel(const SegDesc seg, SeriesEntr
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
         uint32_t filled = 0;
         for (int r = 0; r < seg.nseg; r++) {          // one bulk copy per source segment
-            const uint32_t so = seg.off[r][bkt], sc = seg.off[r][bkt + 1] - so;
+            const uint32_t so = seg.stride ? bkt * seg.stride : seg.off[r][bkt];
+            const uint32_t sc = seg.stride ? n : seg.off[r][bkt + 1] - so;
             if (sc == 0) continue;
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                          :: "r"(smem_u32(s.x) + filled * 32u), "l"(seg.base[r] + so), "r"(sc * 32u), "r"(bar) : "memory");
@@ -1099,22 +1119,24 @@ cudaError_t launch_hist(cudaStream_t st, const ColPtrs &c, uint64_t R, const Row
 {
     if (R == 0) return cudaSuccess;
     const int bshift = 64 - logB;
+    const OptScatter none{0, 0, nullptr, nullptr};
     if (cols_aligned16(c))
-        partition_kernel<false, true><<<partition_grid(R), 256, 0, st>>>(c, R, f, bshift, hist, nullptr);
+        partition_kernel<false, true><<<partition_grid(R), 256, 0, st>>>(c, R, f, bshift, hist, nullptr, none);
     else
-        partition_kernel<false, false><<<partition_grid(R), 256, 0, st>>>(c, R, f, bshift, hist, nullptr);
+        partition_kernel<false, false><<<partition_grid(R), 256, 0, st>>>(c, R, f, bshift, hist, nullptr, none);
     return cudaGetLastError();
 }
 
 cudaError_t launch_scatter(cudaStream_t st, const ColPtrs &c, uint64_t R, const RowFilter &f, int logB, uint32_t *cursor,
-                           Row32 *part)
+                           Row32 *part, uint32_t slot_cap, Row32 *ovf, uint32_t ovf_cap, uint32_t *ovf_count)
 {
     if (R == 0) return cudaSuccess;
     const int bshift = 64 - logB;
+    const OptScatter opt{slot_cap, ovf_cap, ovf, ovf_count};
     if (cols_aligned16(c))
-        partition_kernel<true, true><<<partition_grid(R), 256, 0, st>>>(c, R, f, bshift, cursor, part);
+        partition_kernel<true, true><<<partition_grid(R), 256, 0, st>>>(c, R, f, bshift, cursor, part, opt);
     else
-        partition_kernel<true, false><<<partition_grid(R), 256, 0, st>>>(c, R, f, bshift, cursor, part);
+        partition_kernel<true, false><<<partition_grid(R), 256, 0, st>>>(c, R, f, bshift, cursor, part, opt);
     return cudaGetLastError();
 }
 

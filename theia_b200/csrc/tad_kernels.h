@@ -5,8 +5,12 @@
 namespace tad {
 
 cudaError_t launch_hist(cudaStream_t st, const ColPtrs &c, uint64_t R, const RowFilter &f, int logB, uint32_t *hist);
+// slot_cap == 0: exact mode, cursor[] holds absolute row cursors (from the bucket scan).
+// slot_cap  > 0: optimistic mode, cursor[] counts arrivals from zero, bucket b owns part[b * slot_cap ...); rows past the
+//                slot go to ovf[] (ovf_count may exceed ovf_cap: the caller then falls back to the exact partition).
 cudaError_t launch_scatter(cudaStream_t st, const ColPtrs &c, uint64_t R, const RowFilter &f, int logB, uint32_t *cursor,
-                           Row32 *part);
+                           Row32 *part, uint32_t slot_cap = 0, Row32 *ovf = nullptr, uint32_t ovf_cap = 0,
+                           uint32_t *ovf_count = nullptr);
 cudaError_t launch_bucket_scan(cudaStream_t st, const uint32_t *hist, uint32_t *offsets, uint32_t *cursor, uint32_t B,
                                uint32_t cap, uint32_t *big_list, uint32_t *big_base, uint32_t *cls_list /* 3 x B or null */,
                                uint32_t *stats, void *scan_sync, uint32_t epoch);
@@ -40,9 +44,12 @@ cudaError_t launch_detect_arima(cudaStream_t st, const SeriesEntry *entries, con
 // same per-series arrays / in-place series entries / nsb / npb the group kernel produces.
 // `scratch` must hold spill_scratch_bytes(big_rows) bytes.  Returns launches through *launches.
 size_t spill_scratch_bytes(uint64_t big_rows);
+// Optimistic partition (seg.stride != 0): a listed bucket holds min(count, stride) rows in its slot and the rest in
+// ovf[0, n_ovf) (every overflow row belongs to a listed bucket).
 cudaError_t run_spill(cudaStream_t st, const SegDesc &seg, SeriesEntry *entries, const uint32_t *offsets, const uint32_t *big_list,
                       const uint32_t *big_base, uint32_t n_big, uint64_t big_rows, void *scratch, size_t scratch_bytes,
-                      uint64_t *csr_v, uint32_t *csr_t, uint32_t *nsb, uint32_t *npb, int reducer, int *launches);
+                      uint64_t *csr_v, uint32_t *csr_t, uint32_t *nsb, uint32_t *npb, int reducer, int *launches,
+                      const Row32 *ovf = nullptr, uint32_t n_ovf = 0);
 
 }  // namespace tad
 

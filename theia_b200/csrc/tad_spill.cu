@@ -32,6 +32,19 @@ __global__ void __launch_bounds__(256) spill_gather_kernel(const SegDesc seg, co
     const uint32_t j = blockIdx.x;
     const uint32_t b = big_list[j];
     uint32_t base = big_base[j];
+    if (seg.stride) {
+        // optimistic partition: the slot holds the first `stride` rows; they are packed at j * stride (the
+        // overflow rows follow after all slots; the sort that comes next does not care about input order)
+        const Row32 *rows = seg.base[0] + (size_t)b * seg.stride;
+        for (uint32_t i = threadIdx.x; i < seg.stride; i += blockDim.x) {
+            const Row32 r = rows[i];
+            SpillRow s;
+            s.h = key_hash(r.a, r.b, r.proto);
+            s.a = r.a; s.b = r.b; s.value = r.value; s.proto = r.proto; s.t = r.t;
+            in[(size_t)j * seg.stride + i] = s;
+        }
+        return;
+    }
     for (int sg = 0; sg < seg.nseg; sg++) {
         const uint32_t off = seg.off[sg][b], n = seg.off[sg][b + 1] - off;
         const Row32 *rows = seg.base[sg] + off;
@@ -44,6 +57,17 @@ __global__ void __launch_bounds__(256) spill_gather_kernel(const SegDesc seg, co
         }
         base += n;
     }
+}
+
+__global__ void __launch_bounds__(256) spill_append_kernel(const Row32 *__restrict__ ovf, uint32_t n_ovf, SpillRow *__restrict__ in)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_ovf) return;
+    const Row32 r = ovf[i];
+    SpillRow s;
+    s.h = key_hash(r.a, r.b, r.proto);
+    s.a = r.a; s.b = r.b; s.value = r.value; s.proto = r.proto; s.t = r.t;
+    in[i] = s;
 }
 
 // flags[i] = key_head << 32 | point_head
@@ -140,7 +164,8 @@ size_t spill_scratch_bytes(uint64_t M)
 
 cudaError_t run_spill(cudaStream_t st, const SegDesc &seg, SeriesEntry *entries, const uint32_t *offsets, const uint32_t *big_list,
                       const uint32_t *big_base, uint32_t n_big, uint64_t big_rows, void *scratch, size_t scratch_bytes,
-                      uint64_t *csr_v, uint32_t *csr_t, uint32_t *nsb, uint32_t *npb, int reducer, int *launches)
+                      uint64_t *csr_v, uint32_t *csr_t, uint32_t *nsb, uint32_t *npb, int reducer, int *launches,
+                      const Row32 *ovf, uint32_t n_ovf)
 {
     *launches = 0;
     if (n_big == 0 || big_rows == 0) return cudaSuccess;
@@ -159,6 +184,10 @@ cudaError_t run_spill(cudaStream_t st, const SegDesc &seg, SeriesEntry *entries,
     size_t temp_bytes = cub_temp_bytes(M);
 
     spill_gather_kernel<<<n_big, 256, 0, st>>>(seg, big_list, big_base, in);
+    if (seg.stride) {
+        if ((uint64_t)n_big * seg.stride + n_ovf != big_rows) return cudaErrorInvalidValue;
+        if (n_ovf) spill_append_kernel<<<(n_ovf + 255) / 256, 256, 0, st>>>(ovf, n_ovf, in + (size_t)n_big * seg.stride);
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     size_t tb = temp_bytes;
