@@ -136,7 +136,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": "records/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "EWMA, %d connections x %d points (sample of 100M records / 1M connections)" % (series, args.points),
+        "config": {"workload": "EWMA, %d records / %d connections x %d points per GPU (BASELINE configs[1])" % (args.series * args.points, args.series, args.points),
+                   "sample": "each step runs the CPU path on a bounded sample: %d connections x %d points = %d rows" % (series, args.points, rows),
                    "rows_per_step": rows},
         "cpu_baseline": {"value": v, "unit": "records/s", "cores": cores, "kind": "port",
                          "sample": "%d rows per step, oracle/tad_oracle.c with OpenMP on %d threads" % (rows, cores)},

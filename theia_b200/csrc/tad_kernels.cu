@@ -1,8 +1,10 @@
 // Hand-written sm_100a kernels of the TAD engine.  See DESIGN.md for the pipeline:
 //
 //   hist     (K1)  columns -> key pack -> 64-bit hash -> bucket histogram      reads 17-21 B/row
-//   bscan    (K1b) exclusive scan of the histogram, oversized-bucket list
-//   scatter  (K2)  columns -> 32 B packed rows, hash-partitioned               reads 29, writes 32 B/row
+//                  (exact path only: multi-GPU, or fallback of the optimistic partition)
+//   bscan    (K1b) exclusive scan of the bucket counts, capacity-class lists, oversized-bucket list
+//   scatter  (K2)  columns -> 32 B packed rows, hash-partitioned; on one GPU optimistically
+//                  into fixed-capacity bucket slots with an overflow list      reads 29, writes 32 B/row
 //   group    (K3)  one CTA per bucket: TMA bulk load into shared memory, hash-group by
 //                  key, O(n) bucket-sort of each series by flowEndSeconds, reduce duplicates,
 //                  write per-series arrays + series entries                   reads 32, writes 12 B/row
