@@ -1,0 +1,89 @@
+#!/usr/bin/env python3
+"""Turn the raw ncu outputs of a gpurun call into the committed text summaries.
+
+    ncu --metrics gpu__time_duration.sum --clock-control none -c 100 --csv --log-file gpurun_out/launches_r01_final.csv \\
+        python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e
+    ncu --set full --clock-control none --import-source on -k regex:"group_kernel|partition_kernel|detect_ewma" -s 15 -c 5 \\
+        -o gpurun_out/prof_r01_final python bench.py --steps 1 --warmup 3 --no-cpu --no-e2e
+    ncu -i gpurun_out/prof_r01_final.ncu-rep --page raw --csv > gpurun_out/prof_raw_final.csv
+    python profiles/make_summaries.py
+"""
+import collections
+import csv
+import json
+import os
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = os.path.join(ROOT, "gpurun_out")
+P = os.path.join(ROOT, "profiles")
+
+
+def launch_summary(src, dst, title):
+    rows = list(csv.reader(open(src)))
+    hi = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
+    hdr, data = rows[hi], rows[hi + 1:]
+    ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+    agg = collections.OrderedDict()
+    for r in data:
+        if len(r) <= vi:
+            continue
+        v = float(r[vi].replace(",", ""))
+        v = v / 1e3 if r[ui] == "ns" else (v * 1e3 if r[ui] == "ms" else v)
+        agg.setdefault(r[ki], []).append(v)
+    ours = {k: v for k, v in agg.items() if "tad::" in k or "CUB_" in k}
+    tot = sum(sum(v) for v in ours.values())
+    with open(dst, "w") as f:
+        f.write(title + "\n")
+        f.write("%-110s %5s %12s %7s\n" % ("kernel (engine kernels only; torch data-generation kernels omitted)", "n", "avg us", "share"))
+        for k, v in sorted(ours.items(), key=lambda kv: -sum(kv[1])):
+            f.write("%-110s %5d %12.1f %6.1f%%\n" % (k[:110], len(v), sum(v) / len(v), 100 * sum(v) / tot))
+
+
+def full_summary(src, dst, traffic_dst, title):
+    rows = list(csv.reader(open(src)))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    idx = {h: i for i, h in enumerate(hdr)}
+    want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+            "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+            "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+            "smsp__inst_executed.sum", "launch__registers_per_thread", "launch__occupancy_limit_shared_mem",
+            "launch__occupancy_limit_registers", "launch__grid_size", "launch__block_size", "lts__t_sector_hit_rate.pct"]
+
+    def to_bytes(x, u):
+        x = float(x)
+        return x * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3}.get(u, 1.0)
+
+    traffic = {"rows": 100000000, "source": "ncu --set full --clock-control none, " + os.path.basename(dst), "kernels": {}}
+    grp_r = grp_w = 0.0
+    with open(dst, "w") as f:
+        f.write(title + "\n")
+        for r in data:
+            name = r[idx["Kernel Name"]]
+            f.write("\n%s\n" % name[:160])
+            for w in want:
+                if w in idx:
+                    f.write("  %-62s %s %s\n" % (w, r[idx[w]], units[idx[w]]))
+            rd = to_bytes(r[idx["dram__bytes_read.sum"]], units[idx["dram__bytes_read.sum"]])
+            wr = to_bytes(r[idx["dram__bytes_write.sum"]], units[idx["dram__bytes_write.sum"]])
+            if "group_kernel" in name:
+                grp_r += rd
+                grp_w += wr
+            elif "partition_kernel<1" in name or "partition_kernel<(bool)1" in name:
+                traffic["kernels"]["scatter"] = {"dram_bytes_read": rd, "dram_bytes_write": wr}
+            elif "partition_kernel" in name:
+                traffic["kernels"]["hist"] = {"dram_bytes_read": rd, "dram_bytes_write": wr}
+            elif "detect" in name:
+                traffic["kernels"]["detect"] = {"dram_bytes_read": rd, "dram_bytes_write": wr}
+    traffic["kernels"]["group"] = {"dram_bytes_read": grp_r, "dram_bytes_write": grp_w,
+                                   "note": "sum over the capacity-class launches"}
+    json.dump(traffic, open(traffic_dst, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    launch_summary(os.path.join(G, "launches_r01_final.csv"), os.path.join(P, "r01_launches_final.txt"),
+                   "ncu --metrics gpu__time_duration.sum --clock-control none -c 100; python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e "
+                   "(1e8 rows / 1e6 connections, EWMA); round-1 final pipeline (optimistic partition). Per-launch times are cold-cache "
+                   "and serialised: compare SHARES with bench.py's phase_ms.")
+    full_summary(os.path.join(G, "prof_raw_final.csv"), os.path.join(P, "r01_ncu_full_final.txt"), os.path.join(P, "r01_traffic.json"),
+                 "ncu --set full --clock-control none --import-source on; bench.py --steps 1 --warmup 3 (1e8 rows); round-1 final pipeline")
+    print(open(os.path.join(P, "r01_launches_final.txt")).read()[:1800])

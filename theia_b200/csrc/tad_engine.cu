@@ -953,7 +953,7 @@ int tad_submit(tad_ctx *ctx, const tad_job_spec *spec, const tad_columns *cols, 
     job->t_submit = now_ms();
     job->st.total_stages = kTotalStages;
     *out = job;
-    char msg[256];
+    char msg[200];
     int rc = validate(spec, cols, msg, sizeof(msg));
     if (rc != TAD_OK) {
         // like the controller (controller.go:505-514): illegal arguments are terminal FAILED, never retried
