@@ -68,6 +68,7 @@ struct tad_ctx {
     cudaEvent_t start_ev = nullptr;
     cudaEvent_t x_ev[kMaxXChunks + 1]{};
     int exchange_chunks = kMaxXChunks;
+    bool exchange_chunks_forced = false;     // TAD_EXCHANGE_CHUNKS given: use it at every world size
     uint64_t exchange_min_rows = 1u << 22;   // below this the exchange is not worth chunking (TAD_EXCHANGE_MIN_ROWS)
     std::mutex mu;
     std::condition_variable cv;
@@ -483,7 +484,9 @@ void run_job(tad_ctx *ctx, tad_job *job)
         entries = reinterpret_cast<SeriesEntry *>(part);      // in place over the staged bucket rows
     } else if (world > 1) {
         // ---- multi GPU: K row chunks; chunk c is sent over NVLink (comm stream) while chunk c+1 is scattered ------
-        const int K = R >= ctx->exchange_min_rows ? ctx->exchange_chunks : 1;
+        // chunked (overlapped) exchange pays off at N = 2 (measured 11.5 -> 9.6 ms); at N >= 4 the NVLink all-to-all is
+        // longer than the scatter it could hide behind and the extra segments cost the group kernel more than is won
+        const int K = (R >= ctx->exchange_min_rows && (world == 2 || ctx->exchange_chunks_forced)) ? ctx->exchange_chunks : 1;
         auto xlo = [&](int cidx) -> uint64_t {
             if (cidx <= 0) return 0;
             if (cidx >= K) return R;
@@ -837,6 +840,7 @@ int tad_init(const tad_config *cfg, tad_ctx **out)
     for (int i = 0; ok && i <= kMaxXChunks; i++) ok = cudaEventCreateWithFlags(&ctx->x_ev[i], cudaEventDisableTiming) == cudaSuccess;
     if (const char *e = getenv("TAD_OPTIMISTIC")) ctx->optimistic = atoi(e);
     if (const char *e = getenv("TAD_EXCHANGE_MIN_ROWS")) ctx->exchange_min_rows = strtoull(e, nullptr, 10);
+    if (getenv("TAD_EXCHANGE_CHUNKS")) ctx->exchange_chunks_forced = true;
     if (const char *e = getenv("TAD_EXCHANGE_CHUNKS")) ctx->exchange_chunks = atoi(e) < 1 ? 1 : (atoi(e) > kMaxXChunks ? kMaxXChunks : atoi(e));
     for (int i = 0; ok && i < kMaxEvents; i++) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
     ok = ok && cudaHostAlloc((void **)&ctx->h_stats, 64 * sizeof(uint32_t), cudaHostAllocDefault) == cudaSuccess;

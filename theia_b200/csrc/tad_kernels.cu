@@ -480,18 +480,27 @@ __global__ void __launch_bounds__(NT) group_kernel(const SegDesc seg, SeriesEntr
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (tid == 0) {
+    if (tid < 32) {
+        // one bulk copy per source segment, issued by up to 32 lanes in parallel: every lane fetches the
+        // offsets of its own segment (one round of loads instead of nseg dependent rounds), a warp scan gives
+        // the destination of each piece inside the staged bucket
         const uint32_t bytes = n * 32u;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
-        uint32_t filled = 0;
-        for (int r = 0; r < seg.nseg; r++) {          // one bulk copy per source segment
-            const uint32_t so = seg.stride ? bkt * seg.stride : seg.off[r][bkt];
-            const uint32_t sc = seg.stride ? n : seg.off[r][bkt + 1] - so;
-            if (sc == 0) continue;
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         :: "r"(smem_u32(s.x) + filled * 32u), "l"(seg.base[r] + so), "r"(sc * 32u), "r"(bar) : "memory");
-            filled += sc;
+        if (tid == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+        __syncwarp();
+        uint32_t so = 0, sc = 0;
+        if (tid < seg.nseg) {
+            so = seg.stride ? bkt * seg.stride : seg.off[tid][bkt];
+            sc = seg.stride ? n : seg.off[tid][bkt + 1] - so;
         }
+        uint32_t inc = sc;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+            if (tid >= d) inc += o;
+        }
+        if (sc)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         :: "r"(smem_u32(s.x) + (inc - sc) * 32u), "l"(seg.base[tid] + so), "r"(sc * 32u), "r"(bar) : "memory");
     }
 #pragma unroll
     for (int i = 0; i < SPT; i++) s.ht[tid + i * NT] = 0u;
