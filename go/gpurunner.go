@@ -1,0 +1,174 @@
+//go:build cgo
+
+// Package anomalydetector: GPU job runner behind the function-variable seam of
+// pkg/controller/anomalydetector/controller.go:54-59 (see INTEGRATION.md).  This file is the source a Theia
+// maintainer drops next to controller.go; it is NOT compiled in this repository (no Go toolchain in the build
+// image) -- its behaviour is exercised through the identical Python binding (theia_b200/engine.py,
+// theia_b200/controller.py, tests/test_host_mirror.py).
+package anomalydetector
+
+/*
+#cgo CFLAGS:  -I${SRCDIR}/../../../third_party/theia_tad/include
+#cgo LDFLAGS: -L${SRCDIR}/../../../third_party/theia_tad/lib -ltheia_tad -Wl,-rpath,$ORIGIN
+#include <stdlib.h>
+#include <string.h>
+#include "theia_tad.h"
+*/
+import "C"
+
+import (
+	"fmt"
+	"sync"
+	"unsafe"
+)
+
+// FlowColumns is what the ClickHouse reader hands over: one slice per selected column of default.flows
+// (create_table.sh:31-85), IPs already mapped to u32 (IPv4) or dictionary ids.
+type FlowColumns struct {
+	SrcIP, DstIP, FlowStart, FlowEnd []uint32
+	SrcPort, DstPort                 []uint16
+	Proto                            []uint8
+	Throughput                       []uint64
+}
+
+// JobSpec carries the already validated arguments startSparkApplication would have put into argv
+// (controller.go:530-623).
+type JobSpec struct {
+	Algo       string // EWMA | ARIMA | DBSCAN
+	SumReducer bool   // aggregated-flow modes use sum(throughput), per-connection mode max(throughput)
+	StartTime  uint32 // epoch seconds, 0 = unbounded
+	EndTime    uint32
+	ID         string
+}
+
+// AnomalyRow is one row of default.tadetector (create_table.sh:363-384) minus the per-job constants.
+type AnomalyRow struct {
+	SrcIP, DstIP, FlowStart, FlowEnd  uint32
+	SrcPort, DstPort                  uint16
+	Proto                             uint8
+	StdDev, AlgoCalc, Throughput      float64
+}
+
+type gpuJob struct {
+	job  *C.tad_job
+	cols C.tad_columns
+}
+
+type gpuJobRunner struct {
+	ctx  *C.tad_ctx
+	jobs sync.Map // id -> *gpuJob
+}
+
+func newGPUJobRunner(device int) (*gpuJobRunner, error) {
+	cfg := C.tad_config{device: C.int32_t(device), world_size: 1, rank: 0}
+	var ctx *C.tad_ctx
+	if rc := C.tad_init(&cfg, &ctx); rc != C.TAD_OK {
+		return nil, fmt.Errorf("tad_init: %s", C.GoString(C.tad_strerror(rc)))
+	}
+	return &gpuJobRunner{ctx: ctx}, nil
+}
+
+func algoCode(a string) C.int32_t {
+	switch a {
+	case "ARIMA":
+		return C.TAD_ALGO_ARIMA
+	case "DBSCAN":
+		return C.TAD_ALGO_DBSCAN
+	}
+	return C.TAD_ALGO_EWMA
+}
+
+// Start replaces CreateSparkApplication (controller.go:685): non-blocking submit.
+func (r *gpuJobRunner) Start(spec JobSpec, in *FlowColumns) error {
+	n := len(in.FlowEnd)
+	var cols C.tad_columns
+	if rc := C.tad_alloc_columns(r.ctx, C.uint64_t(n), C.TAD_MEM_HOST, &cols); rc != C.TAD_OK {
+		return fmt.Errorf("tad_alloc_columns: %s", C.GoString(C.tad_strerror(rc)))
+	}
+	// library-owned pinned buffers: the engine never sees a Go pointer
+	copy(unsafe.Slice((*uint32)(unsafe.Pointer(cols.src_ip)), n), in.SrcIP)
+	copy(unsafe.Slice((*uint32)(unsafe.Pointer(cols.dst_ip)), n), in.DstIP)
+	copy(unsafe.Slice((*uint16)(unsafe.Pointer(cols.src_port)), n), in.SrcPort)
+	copy(unsafe.Slice((*uint16)(unsafe.Pointer(cols.dst_port)), n), in.DstPort)
+	copy(unsafe.Slice((*uint8)(unsafe.Pointer(cols.proto)), n), in.Proto)
+	copy(unsafe.Slice((*uint32)(unsafe.Pointer(cols.flow_start)), n), in.FlowStart)
+	copy(unsafe.Slice((*uint32)(unsafe.Pointer(cols.flow_end)), n), in.FlowEnd)
+	copy(unsafe.Slice((*uint64)(unsafe.Pointer(cols.value)), n), in.Throughput)
+	cols.rows = C.uint64_t(n)
+
+	js := C.tad_job_spec{algo: algoCode(spec.Algo), start_time: C.uint32_t(spec.StartTime), end_time: C.uint32_t(spec.EndTime)}
+	if spec.SumReducer {
+		js.reducer = C.TAD_REDUCE_SUM
+	}
+	cid := C.CString(spec.ID)
+	C.strncpy(&js.id[0], cid, 39)
+	C.free(unsafe.Pointer(cid))
+
+	var job *C.tad_job
+	if rc := C.tad_submit(r.ctx, &js, &cols, &job); rc != C.TAD_OK {
+		var st C.tad_status
+		C.tad_poll(job, &st)
+		msg := C.GoString(&st.err_msg[0])
+		C.tad_release(job)
+		C.tad_free_columns(r.ctx, &cols)
+		return illeagelArguementError{fmt.Errorf("%s", msg)} // terminal FAILED, not retried (controller.go:505-514)
+	}
+	r.jobs.Store(spec.ID, &gpuJob{job: job, cols: cols})
+	return nil
+}
+
+// State replaces GetSparkApplication + the Spark-UI stage scraping (controller.go:426-497).
+func (r *gpuJobRunner) State(id string) (state string, completed, total int, errMsg string) {
+	v, ok := r.jobs.Load(id)
+	if !ok {
+		return "", 0, 0, "job not found"
+	}
+	var st C.tad_status
+	C.tad_poll(v.(*gpuJob).job, &st)
+	states := []string{"NEW", "SCHEDULED", "RUNNING", "COMPLETED", "FAILED"} // types.go:33-37
+	return states[st.state], int(st.completed_stages), int(st.total_stages), C.GoString(&st.err_msg[0])
+}
+
+// Results hands every anomalous point to emit; the caller INSERTs into default.tadetector adding aggType /
+// algoType / id / anomaly="true", or the "NO ANOMALY DETECTED" sentinel row when there is none
+// (anomaly_detection.py:395-420).
+func (r *gpuJobRunner) Results(id string, emit func(AnomalyRow)) (int, error) {
+	v, ok := r.jobs.Load(id)
+	if !ok {
+		return 0, fmt.Errorf("job %s not found", id)
+	}
+	var rows C.tad_rows
+	if rc := C.tad_result(v.(*gpuJob).job, &rows); rc != C.TAD_OK {
+		return 0, fmt.Errorf("tad_result: %s", C.GoString(C.tad_strerror(rc)))
+	}
+	n := int(rows.rows)
+	if n == 0 {
+		return 0, nil
+	}
+	srcIP := unsafe.Slice((*uint32)(unsafe.Pointer(rows.src_ip)), n)
+	dstIP := unsafe.Slice((*uint32)(unsafe.Pointer(rows.dst_ip)), n)
+	srcPort := unsafe.Slice((*uint16)(unsafe.Pointer(rows.src_port)), n)
+	dstPort := unsafe.Slice((*uint16)(unsafe.Pointer(rows.dst_port)), n)
+	proto := unsafe.Slice((*uint8)(unsafe.Pointer(rows.proto)), n)
+	fs := unsafe.Slice((*uint32)(unsafe.Pointer(rows.flow_start)), n)
+	fe := unsafe.Slice((*uint32)(unsafe.Pointer(rows.flow_end)), n)
+	sd := unsafe.Slice((*float64)(unsafe.Pointer(rows.stddev)), n)
+	calc := unsafe.Slice((*float64)(unsafe.Pointer(rows.algo_calc)), n)
+	thr := unsafe.Slice((*float64)(unsafe.Pointer(rows.throughput)), n)
+	for i := 0; i < n; i++ {
+		emit(AnomalyRow{srcIP[i], dstIP[i], fs[i], fe[i], srcPort[i], dstPort[i], proto[i], sd[i], calc[i], thr[i]})
+	}
+	return n, nil
+}
+
+// Cancel replaces DeleteSparkApplication (controller.go:385-424).
+func (r *gpuJobRunner) Cancel(id string) {
+	if v, ok := r.jobs.LoadAndDelete(id); ok {
+		j := v.(*gpuJob)
+		C.tad_cancel(j.job)
+		C.tad_release(j.job)
+		C.tad_free_columns(r.ctx, &j.cols)
+	}
+}
+
+func (r *gpuJobRunner) Close() { C.tad_shutdown(r.ctx) }
