@@ -294,3 +294,21 @@ def test_arima_none_series(engine):
     got, st = engine.run(t, algo="ARIMA", emit_all=True)
     assert st["series"] == 4 and sorted(set(got["src_ip"].tolist())) == [103]
     assert len(got["flow_end"]) == 8
+
+
+def test_random_small_tables_with_collisions(engine):
+    """Many tiny tables with few distinct keys: duplicate (key, time) pairs, equal values, u64 values above 2^53 /
+    2^63, both reducers, both detectors -- every column bit-identical to the oracle."""
+    rng = np.random.default_rng(1234)
+    pool = np.array([0, 1, 2, 5, 10**9, 10**9 + 1, 10**9 + 3, 2**53 + 1, 2**63, 2**63 + 2, 2**64 - 1], dtype=np.uint64)
+    for trial in range(40):
+        n = int(rng.integers(1, 80))
+        t = {
+            "src_ip": rng.integers(0, 4, n).astype(np.uint32), "dst_ip": np.zeros(n, dtype=np.uint32),
+            "src_port": rng.integers(0, 3, n).astype(np.uint16), "dst_port": np.zeros(n, dtype=np.uint16),
+            "proto": rng.integers(0, 2, n).astype(np.uint8), "flow_start": np.full(n, 100, dtype=np.uint32),
+            "flow_end": (200 + rng.integers(0, 13, n)).astype(np.uint32),
+            "value": pool[rng.integers(0, len(pool), n)],
+        }
+        algo = "EWMA" if trial % 2 == 0 else "DBSCAN"
+        run_both(engine, t, algo, emit_all=True, reducer=trial % 4 // 2)
