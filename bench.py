@@ -184,7 +184,7 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def step(cols):
-        job = eng.submit(cols, algo="EWMA", tad_id="bench")
+        job = eng.submit(cols, algo=args.algo, tad_id="bench")
         st = job.wait()
         return job, st
 
@@ -339,6 +339,8 @@ def main():
     ap.add_argument("--series", type=int, default=1_000_000)
     ap.add_argument("--points", type=int, default=100)
     ap.add_argument("--ref-series", type=int, default=100_000, help="connections in the CPU sample")
+    ap.add_argument("--algo", default="EWMA", choices=["EWMA", "DBSCAN", "ARIMA"],
+                    help="detector (the BASELINE metric is EWMA; the others are side measurements of configs[2]/[3])")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs: skip the host-buffer leg")
     ap.add_argument("--no-pipelined", action="store_true", help="skip the two-jobs-in-flight e2e figure")
