@@ -37,3 +37,39 @@ def test_struct_sizes_match_header():
     assert ctypes.sizeof(_lib.TadJobSpec) == 24 + 8 + 40
     assert ctypes.sizeof(_lib.TadRows) == 8 + 11 * 8
     assert ctypes.sizeof(_lib.TadStatus) == 16 + 256 + 8 * 8 + 2 * 8 + 9 * 8
+
+
+def test_header_is_valid_c99_and_cxx_and_example_links(tmp_path):
+    """include/theia_tad.h must be consumable from plain C (cgo) and C++; examples/tad_example.c must link against
+    the in-tree library (no GPU needed to link)."""
+    import shutil
+    import subprocess
+    gcc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else shutil.which("gcc")
+    gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else shutil.which("g++")
+    inc = os.path.join(ROOT, "include")
+    hdr = os.path.join(inc, "theia_tad.h")
+    subprocess.check_call([gcc, "-std=c99", "-pedantic", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", hdr])
+    subprocess.check_call([gxx, "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-x", "c++", hdr])
+    exe = str(tmp_path / "tad_example")
+    subprocess.check_call([gcc, "-std=c99", "-Wall", "-I", inc, os.path.join(ROOT, "examples", "tad_example.c"),
+                           "-L", os.path.join(ROOT, "theia_b200"), "-ltheia_tad",
+                           "-Wl,-rpath," + os.path.join(ROOT, "theia_b200"), "-o", exe])
+    assert os.path.exists(exe)
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.gpu
+def test_c_example_runs_on_the_gpu(tmp_path):
+    """The plain-C host (no Python, no torch in the process) drives a job through the C ABI."""
+    import shutil
+    import subprocess
+    gcc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else shutil.which("gcc")
+    exe = str(tmp_path / "tad_example")
+    subprocess.check_call([gcc, "-std=c99", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "tad_example.c"),
+                           "-L", os.path.join(ROOT, "theia_b200"), "-ltheia_tad",
+                           "-Wl,-rpath," + os.path.join(ROOT, "theia_b200"), "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    assert "1 series, 64 points" in out.stdout and "throughput 50007861276" in out.stdout and "6/6 stages" in out.stdout
