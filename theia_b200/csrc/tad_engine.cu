@@ -451,18 +451,7 @@ void run_job(tad_ctx *ctx, tad_job *job)
                 chunk_range(k, lo, hi);
                 CU(cudaStreamWaitEvent(st, ctx->chunk_ev[k], 0));
                 if (hi <= lo) continue;
-                ColPtrs ck = c;
-                if (ck.src_ip) ck.src_ip += lo;
-                if (ck.dst_ip) ck.dst_ip += lo;
-                if (ck.src_port) ck.src_port += lo;
-                if (ck.dst_port) ck.dst_port += lo;
-                if (ck.proto) ck.proto += lo;
-                if (ck.flow_start) ck.flow_start += lo;
-                if (ck.flow_end) ck.flow_end += lo;
-                if (ck.value) ck.value += lo;
-                if (ck.src_ns) ck.src_ns += lo;
-                if (ck.dst_ns) ck.dst_ns += lo;
-                CU(launch_hist(st, ck, hi - lo, f, logB, hist)); launches++;
+                CU(launch_hist(st, offset_cols(lo), hi - lo, f, logB, hist)); launches++;
             }
             mark(TAD_PHASE_H2D);          // copy + overlapped histogram of all chunks
         } else {
@@ -507,23 +496,9 @@ void run_job(tad_ctx *ctx, tad_job *job)
         if (host_input)
             for (int k = 0; k < nchunks; k++) CU(cudaStreamWaitEvent(st, ctx->chunk_ev[k], 0));
         mark(TAD_PHASE_H2D);
-        auto chunk_cols = [&](uint64_t lo) {
-            ColPtrs ck = c;
-            if (ck.src_ip) ck.src_ip += lo;
-            if (ck.dst_ip) ck.dst_ip += lo;
-            if (ck.src_port) ck.src_port += lo;
-            if (ck.dst_port) ck.dst_port += lo;
-            if (ck.proto) ck.proto += lo;
-            if (ck.flow_start) ck.flow_start += lo;
-            if (ck.flow_end) ck.flow_end += lo;
-            if (ck.value) ck.value += lo;
-            if (ck.src_ns) ck.src_ns += lo;
-            if (ck.dst_ns) ck.dst_ns += lo;
-            return ck;
-        };
         for (int cx = 0; cx < K; cx++) {
             const uint64_t lo = xlo(cx), hi = xlo(cx + 1);
-            if (hi > lo) { CU(launch_hist(st, chunk_cols(lo), hi - lo, f, logB, hist + (size_t)cx * B)); launches++; }
+            if (hi > lo) { CU(launch_hist(st, offset_cols(lo), hi - lo, f, logB, hist + (size_t)cx * B)); launches++; }
         }
         mark(TAD_PHASE_HIST);
         for (int cx = 0; cx < K; cx++) {
@@ -555,7 +530,7 @@ void run_job(tad_ctx *ctx, tad_job *job)
         cudaStream_t cs = ctx->copy_stream;
         for (int cx = 0; cx < K; cx++) {
             const uint64_t lo = xlo(cx), hi = xlo(cx + 1);
-            if (hi > lo) { CU(launch_scatter(st, chunk_cols(lo), hi - lo, f, logB, cursor + (size_t)cx * B, part + lo)); launches++; }
+            if (hi > lo) { CU(launch_scatter(st, offset_cols(lo), hi - lo, f, logB, cursor + (size_t)cx * B, part + lo)); launches++; }
             CU(cudaEventRecord(ctx->x_ev[cx], st));
             CU(cudaStreamWaitEvent(cs, ctx->x_ev[cx], 0));
             uint64_t so[kMaxRanks], sb[kMaxRanks], ro[kMaxRanks], rb[kMaxRanks];
@@ -746,6 +721,9 @@ void worker_main(tad_ctx *ctx)
             if (job->cancel.load()) fail(TAD_ERR_CANCELLED, "job cancelled");
             run_job(ctx, job);
         } catch (const JobFail &f) {
+            // nothing of this job may still be reading the caller's columns once it is reported FAILED
+            cudaStreamSynchronize(ctx->copy_stream);
+            cudaStreamSynchronize(ctx->stream);
             cudaGetLastError();
             std::lock_guard<std::mutex> lk(job->mu);
             job->st.state = TAD_STATE_FAILED;
@@ -846,13 +824,13 @@ int tad_init(const tad_config *cfg, tad_ctx **out)
     ok = ok && cudaHostAlloc((void **)&ctx->h_stats, 64 * sizeof(uint32_t), cudaHostAllocDefault) == cudaSuccess;
     ok = ok && cudaHostAlloc((void **)&ctx->h_small, 256 * sizeof(unsigned long long), cudaHostAllocDefault) == cudaSuccess;
     if (!ok) {
-        delete ctx;
+        tad_shutdown(ctx);      // releases whatever was created
         return TAD_ERR_CUDA;
     }
     if (cfg->world_size > 1) {
         int rc = nccl_comm_init(&ctx->nccl, cfg->world_size, cfg->rank, cfg->nccl_unique_id, cfg->nccl_unique_id_bytes);
         if (rc != 0) {
-            delete ctx;
+            tad_shutdown(ctx);
             return TAD_ERR_NCCL;
         }
     }
