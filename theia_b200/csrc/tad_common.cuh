@@ -19,7 +19,7 @@ struct __align__(32) Row32 {
     uint64_t b;       // flow_start << 32 | src_port << 16 | dst_port
     uint64_t value;   // throughput
     uint32_t t;       // flow_end
-    uint32_t proto;
+    uint32_t proto;   // bits 0-7 protocolIdentifier; bits 8-31: the 24 key-hash bits below the bucket bits (hash tag)
 };
 static_assert(sizeof(Row32) == 32, "Row32 must be one 32-byte sector");
 

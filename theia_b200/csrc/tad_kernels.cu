@@ -103,6 +103,13 @@ __device__ __forceinline__ void place_row(const RowRegs &r, uint32_t bucket, uin
 }
 
 
+// The scatter already has the 64-bit key hash in registers: the 24 bits right below the bucket bits travel with
+// the row in the spare bytes of its protocol word, so the group kernel picks its hash slot without hashing again.
+__device__ __forceinline__ uint32_t hash_tag(uint64_t h, int bshift)
+{
+    return (uint32_t)((h << (64 - min(bshift, 64))) >> 40);
+}
+
 template <bool SCATTER>
 __device__ __forceinline__ void emit_row(const RowRegs &r, int bshift, uint32_t *counters, Row32 *part, const OptScatter &o)
 {
@@ -110,7 +117,9 @@ __device__ __forceinline__ void emit_row(const RowRegs &r, int bshift, uint32_t 
     const uint64_t h = key_hash(r.a, r.b, r.proto);
     const uint32_t bucket = bshift >= 64 ? 0u : (uint32_t)(h >> bshift);
     if (SCATTER) {
-        place_row(r, bucket, atomicAdd(&counters[bucket], 1u), part, o);
+        RowRegs rt = r;
+        rt.proto |= hash_tag(h, bshift) << 8;
+        place_row(rt, bucket, atomicAdd(&counters[bucket], 1u), part, o);
     } else {
         atomicAdd(&counters[bucket], 1u);
     }
@@ -185,6 +194,7 @@ __global__ void __launch_bounds__(256) partition_kernel(ColPtrs c, uint64_t R, R
                 for (int i = 0; i < 8; i++) {
                     const uint64_t h = key_hash(r[i].a, r[i].b, r[i].proto);
                     bkt[i] = bshift >= 64 ? 0u : (uint32_t)(h >> bshift);
+                    r[i].proto |= hash_tag(h, bshift) << 8;
                     pos[i] = r[i].keep ? atomicAdd(&counters[bkt[i]], 1u) : 0xffffffffu;
                 }
 #pragma unroll
@@ -452,10 +462,12 @@ __device__ __forceinline__ uint32_t count_lt_u64(const unsigned long long *a, ui
     return c;
 }
 
+constexpr int kSlotHashBits = 13;      // hash-tag bits that pick the shared-memory slot (largest table: 2 * kGroupCap)
+
 template <int CAP, int NT, bool VRANK>
 __global__ void __launch_bounds__(NT) group_kernel(const SegDesc seg, SeriesEntry *__restrict__ entries,
                                                    const uint32_t *__restrict__ offsets, const uint32_t *__restrict__ bucket_list,
-                                                   uint32_t lo_rows, int sshift,
+                                                   uint32_t lo_rows,
                                                    uint64_t *__restrict__ csr_v, uint32_t *__restrict__ csr_t,
                                                    uint32_t *__restrict__ csr_p, uint32_t *__restrict__ nsb,
                                                    uint32_t *__restrict__ npb, int reducer)
@@ -523,11 +535,10 @@ __global__ void __launch_bounds__(NT) group_kernel(const SegDesc seg, SeriesEntr
         myT[j] = 0; myV[j] = 0; mySP[j] = 0;
         if (r < n) {
             const uint4 k = x4[2 * r], w = x4[2 * r + 1];
-            const uint64_t a = pack64(k.x, k.y), b = pack64(k.z, k.w);
-            const uint32_t proto = w.w;
+            const uint32_t proto = w.w;                 // protocol | hash tag << 8 (equal keys carry equal tags)
             myT[j] = w.z;
             myV[j] = pack64(w.x, w.y);
-            uint32_t slot = (uint32_t)(key_hash(a, b, proto) >> sshift) & (HT - 1);
+            uint32_t slot = (proto >> (32 - kSlotHashBits)) & (HT - 1);
             while (true) {
                 uint32_t cur = *reinterpret_cast<volatile uint32_t *>(&s.ht[slot]);
                 if ((cur & 0xffffu) == 0u) {
@@ -573,7 +584,7 @@ __global__ void __launch_bounds__(NT) group_kernel(const SegDesc seg, SeriesEntr
                 // series entry, in place over the (already staged) bucket rows
                 uint4 *e4 = reinterpret_cast<uint4 *>(ent + k);
                 e4[0] = kk;
-                e4[1] = make_uint4(pp, cnt, off_b + so, 0u);
+                e4[1] = make_uint4(pp & 0xffu, cnt, off_b + so, 0u);
             }
         }
     }
@@ -805,11 +816,13 @@ __device__ __forceinline__ void for_each_value(const uint64_t *__restrict__ v, u
 }
 
 // Division by the running count on the Welford critical path.  d / k with k a small integer is computed as
-// q0 = d * r, two FMA residual corrections (r = RN(1/k) from a table filled with __drcp_rn).  With a correctly
-// rounded reciprocal the first correction yields a faithful quotient and the second the correctly rounded one
-// (Markstein's theorem; k < 2^53 - 1 never has an all-ones significand), so the result is bit-identical to
-// IEEE division -- checked against `/` on 6e8 random operands (profiles/microbench/divcheck.c) -- at a fifth of
-// the dependent latency of the generic __ddiv_rn sequence.
+// q0 = d * r (r = RN(1/k) from a table filled with __drcp_rn) plus ONE FMA residual correction
+// q1 = fma(fma(-k, q0, d), r, q0).  That is the correctly rounded quotient: q0 is within 1.5 ulp of z = d/k, so the
+// residual k (z - q0) is exact, and q0 + residual * r = z + (z - q0) * eps with |eps| <= 2^-53 -- a perturbation
+// below 2^-52 ulp(z) -- while z itself keeps a distance of at least ulp(z) / (2k) from every rounding boundary
+// (d - k * midpoint is a non-zero multiple of ulp(z)/2).  So RN(q0 + residual * r) = RN(z) for every k < 2^50.
+// Checked against `/` on 6e8 random and 1.2e9 near-midpoint operands (profiles/microbench/divcheck.c); three
+// dependent operations instead of the ~30 of the generic __ddiv_rn sequence.
 constexpr uint32_t kRcpTable = 4096;
 __device__ double g_rcp[kRcpTable + 1];
 
@@ -832,8 +845,7 @@ __device__ __forceinline__ double series_stddev(const uint64_t *__restrict__ v, 
         double dn;
         if (have_r) {
             const double q0 = __dmul_rn(d, r);
-            const double q1 = __fma_rn(__fma_rn(-cnt, q0, d), r, q0);
-            dn = __fma_rn(__fma_rn(-cnt, q1, d), r, q1);
+            dn = __fma_rn(__fma_rn(-cnt, q0, d), r, q0);
         } else {
             dn = __ddiv_rn(d, cnt);
         }
@@ -1171,7 +1183,7 @@ cudaError_t launch_bucket_scan(cudaStream_t st, const uint32_t *hist, uint32_t *
 
 template <int CAP, int NT, bool VRANK>
 static cudaError_t launch_group_class(cudaStream_t st, const SegDesc &seg, SeriesEntry *entries, const uint32_t *offsets,
-                                      const uint32_t *bucket_list, uint32_t n_buckets, uint32_t lo_rows, int sshift,
+                                      const uint32_t *bucket_list, uint32_t n_buckets, uint32_t lo_rows,
                                       uint64_t *csr_v, uint32_t *csr_t, uint32_t *csr_p, uint32_t *nsb, uint32_t *npb,
                                       int reducer)
 {
@@ -1184,7 +1196,7 @@ static cudaError_t launch_group_class(cudaStream_t st, const SegDesc &seg, Serie
         configured = true;
     }
     if (n_buckets == 0) return cudaSuccess;
-    kern<<<n_buckets, NT, sizeof(S), st>>>(seg, entries, offsets, bucket_list, lo_rows, sshift, csr_v, csr_t, csr_p, nsb, npb,
+    kern<<<n_buckets, NT, sizeof(S), st>>>(seg, entries, offsets, bucket_list, lo_rows, csr_v, csr_t, csr_p, nsb, npb,
                                            reducer);
     return cudaGetLastError();
 }
@@ -1195,7 +1207,7 @@ static cudaError_t launch_group_class(cudaStream_t st, const SegDesc &seg, Serie
 // memory per CTA.  Empty buckets keep the zeroes the caller memset into nsb / npb.
 template <bool VRANK>
 static cudaError_t launch_group_all(cudaStream_t st, const SegDesc &seg, SeriesEntry *entries, const uint32_t *offsets,
-                                    uint32_t B, int sshift, const uint32_t *cls_list, const uint32_t n_cls[3], uint64_t *csr_v,
+                                    uint32_t B, const uint32_t *cls_list, const uint32_t n_cls[3], uint64_t *csr_v,
                                     uint32_t *csr_t, uint32_t *csr_p, uint32_t *nsb, uint32_t *npb, int reducer, int *launches)
 {
     static int small_nt = 0;
@@ -1205,19 +1217,19 @@ static cudaError_t launch_group_all(cudaStream_t st, const SegDesc &seg, SeriesE
     }
     *launches = 0;
     cudaError_t e = small_nt == 128
-                        ? launch_group_class<kGroupCapSmall, 128, VRANK>(st, seg, entries, offsets, cls_list, n_cls[0], 0, sshift,
+                        ? launch_group_class<kGroupCapSmall, 128, VRANK>(st, seg, entries, offsets, cls_list, n_cls[0], 0,
                                                                          csr_v, csr_t, csr_p, nsb, npb, reducer)
-                        : launch_group_class<kGroupCapSmall, 256, VRANK>(st, seg, entries, offsets, cls_list, n_cls[0], 0, sshift,
+                        : launch_group_class<kGroupCapSmall, 256, VRANK>(st, seg, entries, offsets, cls_list, n_cls[0], 0,
                                                                          csr_v, csr_t, csr_p, nsb, npb, reducer);
     *launches += n_cls[0] ? 1 : 0;
     if (e == cudaSuccess && n_cls[1]) {
-        e = launch_group_class<kGroupCapMid, 256, VRANK>(st, seg, entries, offsets, cls_list + B, n_cls[1], kGroupCapSmall, sshift,
+        e = launch_group_class<kGroupCapMid, 256, VRANK>(st, seg, entries, offsets, cls_list + B, n_cls[1], kGroupCapSmall,
                                                          csr_v, csr_t, csr_p, nsb, npb, reducer);
         ++*launches;
     }
     if (e == cudaSuccess && n_cls[2]) {
         e = launch_group_class<kGroupCap, 512, VRANK>(st, seg, entries, offsets, cls_list + 2 * (size_t)B, n_cls[2], kGroupCapMid,
-                                                      sshift, csr_v, csr_t, csr_p, nsb, npb, reducer);
+                                                      csr_v, csr_t, csr_p, nsb, npb, reducer);
         ++*launches;
     }
     return e;
@@ -1227,11 +1239,10 @@ cudaError_t launch_group(cudaStream_t st, const SegDesc &seg, SeriesEntry *entri
                          int logB, const uint32_t *cls_list, const uint32_t n_cls[3], uint64_t *csr_v, uint32_t *csr_t,
                          uint32_t *csr_p, uint32_t *nsb, uint32_t *npb, int reducer, int *launches)
 {
-    int sshift = 64 - logB - 13;          // 13 hash bits below the bucket bits pick the slot
-    if (sshift < 0) sshift = 0;
-    return csr_p ? launch_group_all<true>(st, seg, entries, offsets, B, sshift, cls_list, n_cls, csr_v, csr_t, csr_p, nsb, npb,
+    (void)logB;        // the slot hash bits travel with the rows (hash_tag)
+    return csr_p ? launch_group_all<true>(st, seg, entries, offsets, B, cls_list, n_cls, csr_v, csr_t, csr_p, nsb, npb,
                                           reducer, launches)
-                 : launch_group_all<false>(st, seg, entries, offsets, B, sshift, cls_list, n_cls, csr_v, csr_t, csr_p, nsb, npb,
+                 : launch_group_all<false>(st, seg, entries, offsets, B, cls_list, n_cls, csr_v, csr_t, csr_p, nsb, npb,
                                            reducer, launches);
 }
 

@@ -26,6 +26,16 @@ struct SpillDecomposer {
     }
 };
 
+// part[] rows carry hash-tag bits above the protocol byte (see hash_tag in tad_kernels.cu): strip them here
+__device__ __forceinline__ SpillRow to_spill(const Row32 &r)
+{
+    SpillRow s;
+    s.proto = r.proto & 0xffu;
+    s.h = key_hash(r.a, r.b, s.proto);
+    s.a = r.a; s.b = r.b; s.value = r.value; s.t = r.t;
+    return s;
+}
+
 __global__ void __launch_bounds__(256) spill_gather_kernel(const SegDesc seg, const uint32_t *__restrict__ big_list,
                                                            const uint32_t *__restrict__ big_base, SpillRow *__restrict__ in)
 {
@@ -37,11 +47,7 @@ __global__ void __launch_bounds__(256) spill_gather_kernel(const SegDesc seg, co
         // overflow rows follow after all slots; the sort that comes next does not care about input order)
         const Row32 *rows = seg.base[0] + (size_t)b * seg.stride;
         for (uint32_t i = threadIdx.x; i < seg.stride; i += blockDim.x) {
-            const Row32 r = rows[i];
-            SpillRow s;
-            s.h = key_hash(r.a, r.b, r.proto);
-            s.a = r.a; s.b = r.b; s.value = r.value; s.proto = r.proto; s.t = r.t;
-            in[(size_t)j * seg.stride + i] = s;
+            in[(size_t)j * seg.stride + i] = to_spill(rows[i]);
         }
         return;
     }
@@ -49,11 +55,7 @@ __global__ void __launch_bounds__(256) spill_gather_kernel(const SegDesc seg, co
         const uint32_t off = seg.off[sg][b], n = seg.off[sg][b + 1] - off;
         const Row32 *rows = seg.base[sg] + off;
         for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-            const Row32 r = rows[i];
-            SpillRow s;
-            s.h = key_hash(r.a, r.b, r.proto);
-            s.a = r.a; s.b = r.b; s.value = r.value; s.proto = r.proto; s.t = r.t;
-            in[base + i] = s;
+            in[base + i] = to_spill(rows[i]);
         }
         base += n;
     }
@@ -63,11 +65,7 @@ __global__ void __launch_bounds__(256) spill_append_kernel(const Row32 *__restri
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_ovf) return;
-    const Row32 r = ovf[i];
-    SpillRow s;
-    s.h = key_hash(r.a, r.b, r.proto);
-    s.a = r.a; s.b = r.b; s.value = r.value; s.proto = r.proto; s.t = r.t;
-    in[i] = s;
+    in[i] = to_spill(ovf[i]);
 }
 
 // flags[i] = key_head << 32 | point_head
