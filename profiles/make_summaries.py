@@ -85,5 +85,7 @@ if __name__ == "__main__":
                    "(1e8 rows / 1e6 connections, EWMA); round-1 final pipeline (optimistic partition). Per-launch times are cold-cache "
                    "and serialised: compare SHARES with bench.py's phase_ms.")
     full_summary(os.path.join(G, "prof_raw_final.csv"), os.path.join(P, "r01_ncu_full_final.txt"), os.path.join(P, "r01_traffic.json"),
-                 "ncu --set full --clock-control none --import-source on; bench.py --steps 1 --warmup 3 (1e8 rows); round-1 final pipeline")
+                 "ncu --set full --clock-control none --import-source on; bench.py --steps 1 --warmup 3 (1e8 rows); round-1 final pipeline "
+                 "(captured with the group kernel reading {bucket, rows, offset} from a 16-byte class-list entry; that variant was 0.08 ms "
+                 "slower inside the pipeline and the shipped kernel reads bucket_list + offsets[] again -- the kernel body is otherwise identical)")
     print(open(os.path.join(P, "r01_launches_final.txt")).read()[:1800])

@@ -22,20 +22,10 @@ constexpr double kDiffuse = 1e6;
 constexpr double kLog2Pi = 1.8378770664093454835606594728112;
 constexpr int kLbfgsM = 12;
 
-__device__ __forceinline__ uint32_t find_bucket_a(const uint32_t *__restrict__ sbase, uint32_t B, uint32_t i)
-{
-    uint32_t lo = 0, hi = B;
-    while (hi - lo > 1) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (sbase[mid] <= i) lo = mid; else hi = mid;
-    }
-    return lo;
-}
-
 __device__ __forceinline__ SeriesEntry load_entry(const SeriesEntry *entries, const uint32_t *offsets, const uint32_t *sbase,
                                                   uint32_t B, uint32_t i)
 {
-    const uint32_t b = find_bucket_a(sbase, B, i);
+    const uint32_t b = find_bucket(sbase, B, i);
     const uint4 *p = reinterpret_cast<const uint4 *>(entries + offsets[b] + (i - sbase[b]));
     const uint4 k = p[0], w = p[1];
     SeriesEntry e;

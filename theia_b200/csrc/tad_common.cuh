@@ -100,4 +100,19 @@ constexpr int kGroupTarget = 768;     // mean rows per bucket pick_logb aims for
 constexpr int kGroupThreads = 256;
 constexpr int kGroupHT = 2 * kGroupCap;
 
+
+// sbase[] layout (written by the series scan): [0, B] exclusive scan of series per bucket (sbase[B] = S), followed by the
+// bucket hint table: hint[j] = bucket of series 32 * j.  A detector finds the bucket of series i with one hint load and a
+// short forward walk (32 series span a handful of buckets) instead of a log2(B)-deep chain of dependent loads.
+constexpr uint32_t kHintStride = 32;
+__host__ __device__ __forceinline__ size_t sbase_words(uint32_t B, uint64_t max_series) { return (size_t)B + 1 + max_series / kHintStride + 2; }
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t find_bucket(const uint32_t *__restrict__ sbase, uint32_t B, uint32_t i)
+{
+    uint32_t b = sbase[B + 1 + i / kHintStride];      // bucket of series (i rounded down to a multiple of 32) <= bucket of i
+    while (sbase[b + 1] <= i) b++;                     // terminates: sbase[B] = S > i
+    return b;
+}
+#endif
+
 }  // namespace tad

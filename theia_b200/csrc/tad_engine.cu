@@ -362,13 +362,11 @@ void run_job(tad_ctx *ctx, tad_job *job)
     ensure(ctx->cls_list, (size_t)B * 4 * 3);
     ensure(ctx->nsb, (size_t)Bl * 4);
     ensure(ctx->npb, (size_t)Bl * 4);
-    ensure(ctx->sbase, ((size_t)Bl + 1) * 4);
     ensure(ctx->part, (R ? R : 1) * sizeof(Row32));
     uint32_t *hist = (uint32_t *)ctx->hist.p, *offsets = (uint32_t *)ctx->offsets.p, *cursor = (uint32_t *)ctx->cursor.p;
     uint32_t *big_base = (uint32_t *)ctx->big_base.p;
     uint32_t *cls_list = (uint32_t *)ctx->cls_list.p;
     uint32_t *big_list = (uint32_t *)ctx->big_list.p, *nsb = (uint32_t *)ctx->nsb.p, *npb = (uint32_t *)ctx->npb.p;
-    uint32_t *sbase = (uint32_t *)ctx->sbase.p;
     Row32 *part = (Row32 *)ctx->part.p;
 
     CU(cudaMemsetAsync(nsb, 0, (size_t)Bl * 4, st));
@@ -594,6 +592,8 @@ void run_job(tad_ctx *ctx, tad_job *job)
         launches += l;
         mark(TAD_PHASE_SPILL);
     }
+    ensure(ctx->sbase, sbase_words(Bl, cap_rows) * 4);      // series base per bucket + bucket hint per 32 series
+    uint32_t *sbase = (uint32_t *)ctx->sbase.p;
     CU(launch_series_scan(st, nsb, npb, sbase, Bl, d_stats, ctx->scan_sync.p, ++ctx->scan_epoch)); launches++;
     CU(cudaMemcpyAsync(ctx->h_stats, d_stats, ST_COUNT * 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));

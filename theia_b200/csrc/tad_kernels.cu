@@ -354,7 +354,7 @@ __global__ void __launch_bounds__(1024) bucket_scan_kernel(const uint32_t *__res
     if (threadIdx.x == 0) atomicMax(&stats[ST_MAXBUCKET], maxb_s);
 }
 
-// sbase[B+1] = exclusive scan of series-per-bucket; also totals points.
+// sbase[B+1] = exclusive scan of series-per-bucket, followed by the bucket hint table; also totals points.
 __global__ void __launch_bounds__(1024) series_scan_kernel(const uint32_t *__restrict__ nsb, const uint32_t *__restrict__ npb,
                                                            uint32_t *__restrict__ sbase, uint32_t B, uint32_t *__restrict__ stats,
                                                            ScanSync *sy, uint32_t epoch)
@@ -376,7 +376,13 @@ __global__ void __launch_bounds__(1024) series_scan_kernel(const uint32_t *__res
     unsigned long long before[4], all[4];
     grid_prefix(sy, epoch, mine, before, all);
     uint32_t run = (uint32_t)before[0] + pre;
-    for (uint32_t i = lo; i < hi; i++) { sbase[i] = run; run += nsb[i]; }
+    uint32_t *hint = sbase + B + 1;                 // hint[j] = bucket of series 32 * j (tad_common.cuh)
+    for (uint32_t i = lo; i < hi; i++) {
+        const uint32_t ns = nsb[i];
+        sbase[i] = run;
+        for (uint32_t m = (run + kHintStride - 1) & ~(kHintStride - 1); m < run + ns; m += kHintStride) hint[m / kHintStride] = i;
+        run += ns;
+    }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         sbase[B] = (uint32_t)all[0];
         stats[ST_SERIES] = (uint32_t)all[0];
@@ -748,29 +754,21 @@ __global__ void __launch_bounds__(NT) group_kernel(const SegDesc seg, SeriesEntr
 // ----------------------------------------------------------------------------------------
 // K4: detect -- one thread per series
 // ----------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t find_bucket(const uint32_t *__restrict__ sbase, uint32_t B, uint32_t i)
-{
-    // largest b in [0, B) with sbase[b] <= i  (sbase is non-decreasing, sbase[B] = S > i)
-    uint32_t lo = 0, hi = B;
-    while (hi - lo > 1) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (sbase[mid] <= i) lo = mid; else hi = mid;
-    }
-    return lo;
-}
-
 // Bucket of series `i` for every thread of a CTA whose threads hold consecutive series: one thread searches
 // the bucket of the CTA's first series, a window of sbase[] starting there is staged in shared memory, and
 // each thread finishes with a short search inside the window (global binary search only if it falls outside).
 constexpr int kBucketWindow = 256;
-__device__ __forceinline__ uint32_t find_bucket_cta(const uint32_t *__restrict__ sbase, uint32_t B, uint32_t i, uint32_t i_first,
-                                                    uint32_t *win /* kBucketWindow + 1 */, uint32_t *b0_s)
+__device__ __forceinline__ uint32_t find_bucket_cta(const uint32_t *__restrict__ sbase, const uint32_t *__restrict__ offsets, uint32_t B,
+                                                    uint32_t i, uint32_t i_first, uint32_t *win /* kBucketWindow + 1 */,
+                                                    uint32_t *woff /* kBucketWindow + 1 */, uint32_t *b0_s)
 {
     if (threadIdx.x == 0) *b0_s = find_bucket(sbase, B, i_first);
     __syncthreads();
     const uint32_t b0 = *b0_s;
-    for (uint32_t k = threadIdx.x; k <= (uint32_t)kBucketWindow; k += blockDim.x)
+    for (uint32_t k = threadIdx.x; k <= (uint32_t)kBucketWindow; k += blockDim.x) {
         win[k] = b0 + k <= B ? sbase[b0 + k] : 0xffffffffu;
+        woff[k] = b0 + k <= B ? offsets[b0 + k] : 0u;      // same round trip: the entry address needs both
+    }
     __syncthreads();
     if (win[kBucketWindow] <= i) return find_bucket(sbase, B, i);      // beyond the window (many empty buckets)
     uint32_t lo = 0, hi = kBucketWindow;                                // win[lo] <= i < win[hi]
@@ -897,7 +895,7 @@ struct DetectSmem {
     uint32_t ent_proto[kDetectThreads];
     alignas(8) unsigned long long mbar;
     uint32_t span_lo, span_hi, qcount, base, b0;
-    uint32_t win[kBucketWindow + 1];
+    uint32_t win[kBucketWindow + 1], woff[kBucketWindow + 1];
 };
 
 template <int NT, bool STAGED>
@@ -919,10 +917,12 @@ __global__ void __launch_bounds__(NT) detect_ewma_kernel(const SeriesEntry *__re
     __syncthreads();
     SeriesEntry e;
     e.n = 0; e.off = 0; e.a = 0; e.b = 0; e.proto = 0;
-    const uint32_t bkt = find_bucket_cta(sbase, B, i < S ? i : S - 1, blockIdx.x * NT, sm.win, &sm.b0);
+    const uint32_t bkt = find_bucket_cta(sbase, offsets, B, i < S ? i : S - 1, blockIdx.x * NT, sm.win, sm.woff, &sm.b0);
     if (i < S) {
-        const uint32_t b = bkt;
-        const uint4 *p = reinterpret_cast<const uint4 *>(entries + offsets[b] + (i - sbase[b]));
+        const uint32_t b = bkt, wk = b - sm.b0;
+        const bool inwin = wk < (uint32_t)kBucketWindow;
+        const uint32_t ob = inwin ? sm.woff[wk] : offsets[b], sb = inwin ? sm.win[wk] : sbase[b];
+        const uint4 *p = reinterpret_cast<const uint4 *>(entries + ob + (i - sb));
         const uint4 k = p[0], w = p[1];
         e.a = pack64(k.x, k.y); e.b = pack64(k.z, k.w); e.proto = w.x; e.n = w.y; e.off = w.z;
     }
