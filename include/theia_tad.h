@@ -202,6 +202,25 @@ int tad_abi_version(void);
  * it to tad_init.  Replaces: Spark's driver/executor rendezvous (no reference call site). */
 int tad_get_unique_id(void *out, size_t bytes);
 
+/* ---- ClickHouse Native-format helpers (host only: no GPU, no context) -----------------------------------------
+ * The reference job moves rows over JDBC (read: anomaly_detection.py:655-662; write: :713-726).  The shim streams
+ * `SELECT ... FORMAT Native` column blocks instead (clickhouse-go, go.mod:7) and copies every fixed-width column
+ * (UInt8/16/64, DateTime = UInt32; create_table.sh:31-85) straight into the tad_columns buffers.  Only String
+ * columns need work: these three calls index them, turn IPv4 text into the u32 key column and back.
+ * theia_b200/clickhouse_native.py is the block reader / writer built on them. */
+
+/* A String column of `rows` values is rows x (VarUInt length, bytes).  Writes the payload position and length of
+ * every value and the number of bytes consumed.  TAD_ERR_INVALID_ARG if the buffer ends early or a length >= 2^32. */
+int tad_ch_string_index(const uint8_t *buf, size_t len, uint64_t rows, uint64_t *offsets, uint32_t *lengths,
+                        size_t *consumed);
+/* "a.b.c.d" -> a<<24 | b<<16 | c<<8 | d.  is_v4[i] = 0 (and out[i] = 0) for anything else (IPv6, empty, names):
+ * the caller gives those rows dictionary ids.  sourceIP / destinationIP are String columns (create_table.sh:38-39). */
+int tad_ch_parse_ipv4(const uint8_t *buf, const uint64_t *offsets, const uint32_t *lengths, uint64_t rows,
+                      uint32_t *out, uint8_t *is_v4);
+/* u32 -> String column bytes (VarUInt length + "a.b.c.d" per row) for the tadetector INSERT (create_table.sh:363-384).
+ * Needs at most 16 bytes per row; TAD_ERR_INVALID_ARG if out_cap is too small. */
+int tad_ch_format_ipv4(const uint32_t *ips, uint64_t rows, uint8_t *out, size_t out_cap, size_t *written);
+
 #ifdef __cplusplus
 }
 #endif

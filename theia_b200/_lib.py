@@ -19,7 +19,8 @@ TAD_REDUCE_MAX, TAD_REDUCE_SUM = 0, 1
 
 EXPORTS = ("tad_abi_version", "tad_strerror", "tad_init", "tad_shutdown", "tad_alloc_columns",
            "tad_free_columns", "tad_submit", "tad_poll", "tad_wait", "tad_result", "tad_cancel",
-           "tad_release", "tad_get_unique_id", "tad_alloc_ns_columns")
+           "tad_release", "tad_get_unique_id", "tad_alloc_ns_columns", "tad_ch_string_index", "tad_ch_parse_ipv4",
+           "tad_ch_format_ipv4")
 
 
 class TadConfig(C.Structure):
@@ -82,5 +83,8 @@ def load():
     L.tad_cancel.argtypes = [C.c_void_p]
     L.tad_release.argtypes = [C.c_void_p]
     L.tad_get_unique_id.argtypes = [C.c_void_p, C.c_size_t]
+    L.tad_ch_string_index.argtypes = [C.c_void_p, C.c_size_t, C.c_uint64, C.c_void_p, C.c_void_p, C.POINTER(C.c_size_t)]
+    L.tad_ch_parse_ipv4.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+    L.tad_ch_format_ipv4.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     _lib = L
     return L

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtheia_tad.so")
-SOURCES = ["tad_kernels.cu", "tad_spill.cu", "tad_arima.cu", "tad_engine.cu", "tad_nccl.cu"]
+SOURCES = ["tad_kernels.cu", "tad_spill.cu", "tad_arima.cu", "tad_engine.cu", "tad_nccl.cu", "tad_chnative.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-Wno-format-truncation"]
 
