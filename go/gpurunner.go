@@ -172,3 +172,27 @@ func (r *gpuJobRunner) Cancel(id string) {
 }
 
 func (r *gpuJobRunner) Close() { C.tad_shutdown(r.ctx) }
+
+// ipColumnFromNative turns the data part of a Native-format String column (sourceIP / destinationIP of a
+// `SELECT ... FORMAT Native` block, create_table.sh:38-39) into the u32 key column.  isV4[i] == false marks rows
+// whose text is not a dotted quad (IPv6, empty): the caller gives those dictionary ids.  Returns the number of
+// bytes of buf the column occupied.
+func ipColumnFromNative(buf []byte, rows int) (ips []uint32, isV4 []bool, used int, err error) {
+	offsets := make([]uint64, rows)
+	lengths := make([]uint32, rows)
+	var n C.size_t
+	if rc := C.tad_ch_string_index((*C.uint8_t)(unsafe.Pointer(&buf[0])), C.size_t(len(buf)), C.uint64_t(rows),
+		(*C.uint64_t)(unsafe.Pointer(&offsets[0])), (*C.uint32_t)(unsafe.Pointer(&lengths[0])), &n); rc != C.TAD_OK {
+		return nil, nil, 0, fmt.Errorf("malformed String column: %s", C.GoString(C.tad_strerror(rc)))
+	}
+	ips = make([]uint32, rows)
+	flags := make([]uint8, rows)
+	C.tad_ch_parse_ipv4((*C.uint8_t)(unsafe.Pointer(&buf[0])), (*C.uint64_t)(unsafe.Pointer(&offsets[0])),
+		(*C.uint32_t)(unsafe.Pointer(&lengths[0])), C.uint64_t(rows), (*C.uint32_t)(unsafe.Pointer(&ips[0])),
+		(*C.uint8_t)(unsafe.Pointer(&flags[0])))
+	isV4 = make([]bool, rows)
+	for i, f := range flags {
+		isV4[i] = f != 0
+	}
+	return ips, isV4, int(n), nil
+}
