@@ -11,7 +11,6 @@ set -u
 mkdir -p gpurun_out
 timeout 120 python -m pytest tests -m gpu -x -q > gpurun_out/ab_tests.log 2>&1; echo "rc=$?" >> gpurun_out/ab_tests.log
 tail -3 gpurun_out/ab_tests.log
-run() { timeout 60 python bench.py --no-cpu --no-e2e "$@" > "gpurun_out/ab_$1.json" 2> "gpurun_out/ab_$1.err"; }
 cp theia_b200/libtheia_tad.so /tmp/ab_new.so
 timeout 60 python bench.py --no-cpu --no-e2e > gpurun_out/ab_new.json 2> gpurun_out/ab_new.err
 if [ -f theia_b200/libtheia_tad_prev.so ]; then
