@@ -17,8 +17,10 @@
 // results are bit-identical to the CPU oracle (no FMA contraction).
 #include "tad_kernels.h"
 
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
+#include <mutex>
 
 namespace tad {
 
@@ -1111,16 +1113,20 @@ __global__ void __launch_bounds__(NT) detect_dbscan_kernel(const SeriesEntry *__
 // ----------------------------------------------------------------------------------------
 // launchers
 // ----------------------------------------------------------------------------------------
-static int g_num_sms = 0;
+// The launchers are called from one worker thread per context; several contexts may live in one process
+// (bench.py keeps two jobs in flight), so the lazily initialised process-wide values below are atomics.
+static std::atomic<int> g_num_sms{0};
 static int num_sms()
 {
-    if (!g_num_sms) {
+    int n = g_num_sms.load(std::memory_order_relaxed);
+    if (!n) {
         int dev = 0;
         cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (g_num_sms <= 0) g_num_sms = 148;
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+        g_num_sms.store(n, std::memory_order_relaxed);
     }
-    return g_num_sms;
+    return n;
 }
 
 static bool cols_aligned16(const ColPtrs &c)
@@ -1188,12 +1194,12 @@ static cudaError_t launch_group_class(cudaStream_t st, const SegDesc &seg, Serie
                                       int reducer)
 {
     using S = GroupSmem<CAP, NT>;
-    static bool configured = false;
+    static std::atomic<bool> configured{false};
     auto kern = group_kernel<CAP, NT, VRANK>;
-    if (!configured) {
+    if (!configured.load(std::memory_order_acquire)) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(S));
         if (e != cudaSuccess) return e;
-        configured = true;
+        configured.store(true, std::memory_order_release);
     }
     if (n_buckets == 0) return cudaSuccess;
     kern<<<n_buckets, NT, sizeof(S), st>>>(seg, entries, offsets, bucket_list, lo_rows, csr_v, csr_t, csr_p, nsb, npb,
@@ -1210,10 +1216,12 @@ static cudaError_t launch_group_all(cudaStream_t st, const SegDesc &seg, SeriesE
                                     uint32_t B, const uint32_t *cls_list, const uint32_t n_cls[3], uint64_t *csr_v,
                                     uint32_t *csr_t, uint32_t *csr_p, uint32_t *nsb, uint32_t *npb, int reducer, int *launches)
 {
-    static int small_nt = 0;
+    static std::atomic<int> small_nt_s{0};
+    int small_nt = small_nt_s.load(std::memory_order_relaxed);
     if (!small_nt) {
         const char *ev = getenv("TAD_GROUP_NT");          // tuning knob: threads per CTA of the first capacity class
         small_nt = ev ? atoi(ev) : 256;
+        small_nt_s.store(small_nt, std::memory_order_relaxed);
     }
     *launches = 0;
     cudaError_t e = small_nt == 128
@@ -1255,12 +1263,11 @@ cudaError_t launch_series_scan(cudaStream_t st, const uint32_t *nsb, const uint3
 
 static void ensure_rcp_table(cudaStream_t st)
 {
-    static bool done = false;
-    if (!done) {
+    static std::once_flag once;       // a second context waits here until the table is complete
+    std::call_once(once, [&] {
         rcp_table_kernel<<<(kRcpTable + 256) / 256, 256, 0, st>>>();
         cudaStreamSynchronize(st);      // once per process: other contexts (streams) of this device read the table too
-        done = true;
-    }
+    });
 }
 
 cudaError_t launch_detect_ewma(cudaStream_t st, const SeriesEntry *entries, const uint32_t *offsets, const uint32_t *sbase, uint32_t B,
@@ -1269,13 +1276,15 @@ cudaError_t launch_detect_ewma(cudaStream_t st, const SeriesEntry *entries, cons
 {
     if (S == 0) return cudaSuccess;
     constexpr int NT = kDetectThreads;
-    static int staged = -1;
+    static std::atomic<int> staged_s{-1};
+    int staged = staged_s.load(std::memory_order_acquire);
     if (staged < 0) {
         const char *ev = getenv("TAD_DETECT_STAGED");        // tuning knob: 1 = TMA-staged span (2 CTAs/SM), 0 = global loads at full occupancy
         staged = ev ? atoi(ev) : 1;
         cudaError_t e = cudaFuncSetAttribute(detect_ewma_kernel<NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)sizeof(DetectSmem<true>));
         if (e != cudaSuccess) return e;
+        staged_s.store(staged, std::memory_order_release);
     }
     ensure_rcp_table(st);
     if (staged)
