@@ -112,6 +112,24 @@ def ncu_traffic(kernel, rows):
     return None
 
 
+def python_port_rate(points):
+    """Single-core rate of the pure-Python restatement (numpy stages A/B + the per-series UDF loops the Spark workers
+    would run, oracle/tad_oracle.py) on a 2e5-row sample: the 'local[1]'-style figure SURVEY section 8(d) asks for.
+    Reported next to the C port; never fatal."""
+    try:
+        from oracle import tad_oracle
+        from theia_b200 import synth
+        t = synth.make_flows(max(1, 200_000 // points), points, seed=1)
+        tad_oracle.run_job(t, tad_oracle.JobSpec())
+        t0 = time.perf_counter()
+        tad_oracle.run_job(t, tad_oracle.JobSpec())
+        dt = time.perf_counter() - t0
+        return {"value": len(t["value"]) / dt, "unit": "records/s", "cores": 1,
+                "sample": "%d rows, oracle/tad_oracle.py" % len(t["value"])}
+    except Exception as e:       # the bench line must not depend on this side figure
+        return {"unavailable": repr(e)[:120]}
+
+
 def run_reference(args):
     """CPU arm: the oracle port with all host threads on a bounded sample of the same workload."""
     import numpy as np
@@ -140,7 +158,8 @@ def run_reference(args):
                    "sample": "each step runs the CPU path on a bounded sample: %d connections x %d points = %d rows" % (series, args.points, rows),
                    "rows_per_step": rows},
         "cpu_baseline": {"value": v, "unit": "records/s", "cores": cores, "kind": "port",
-                         "sample": "%d rows per step, oracle/tad_oracle.c with OpenMP on %d threads" % (rows, cores)},
+                         "sample": "%d rows per step, oracle/tad_oracle.c with OpenMP on %d threads" % (rows, cores),
+                         "python_port_1core": python_port_rate(args.points)},
         "e2e": {"value": v, "unit": "records/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
 
@@ -322,7 +341,8 @@ def run_ours(args):
                 c_oracle.run_job(t, algo=0, threads=cores)
             dt = (time.perf_counter() - t0) / reps
             line["cpu_baseline"] = {"value": len(t["value"]) / dt, "unit": "records/s", "cores": cores, "kind": "port",
-                                    "sample": "%d rows x %d reps, oracle/tad_oracle.c OpenMP" % (len(t["value"]), reps)}
+                                    "sample": "%d rows x %d reps, oracle/tad_oracle.c OpenMP" % (len(t["value"]), reps),
+                                    "python_port_1core": python_port_rate(n)}
         print(json.dumps(line))
     hcols.free()
     eng.close()
