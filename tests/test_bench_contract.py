@@ -35,6 +35,8 @@ def test_reference_arm_runs_on_cpu():
     assert d["impl"] == "reference" and BASE_KEYS <= set(d)
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"]
+    py = d["cpu_baseline"]["python_port_1core"]          # single-core pure-Python restatement, reported beside the C port
+    assert py["cores"] == 1 and 0 < py["value"] < d["value"] * 50
     # ranks other than 0 print nothing and exit 0
     env = dict(os.environ, RANK="1")
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
