@@ -186,3 +186,26 @@ def test_decode_rate_is_reported():
     dt = time.perf_counter() - t0
     assert np.array_equal(d["sourceIP"], t["src_ip"]) and np.array_equal(d["throughput"], t["value"])
     print("native decode: %.1f M rows/s, %.0f MB/s" % (len(t["value"]) / dt / 1e6, len(stream) / dt / 1e6))
+
+
+def test_mutated_streams_never_crash_the_decoder():
+    """Bit flips and truncations of a valid stream either decode or raise ValueError / NotImplementedError -- the C index
+    walks attacker-controlled lengths, so it must never read outside the buffer."""
+    from hypothesis import given, settings, strategies as st
+    flows = _named_flows(seed=3, series=6, points=4)
+    good = _flows_as_native(flows, block_rows=10)
+
+    @settings(max_examples=300, deadline=None)
+    @given(st.lists(st.tuples(st.integers(0, len(good) - 1), st.integers(0, 255)), min_size=1, max_size=6),
+           st.integers(0, len(good)))
+    def run(muts, cut):
+        b = bytearray(good)
+        for pos, val in muts:
+            b[pos] = val
+        data = bytes(b[:cut]) if cut else bytes(b)
+        try:
+            chn.flows_from_native(data)
+        except (ValueError, NotImplementedError):
+            pass
+
+    run()

@@ -145,6 +145,8 @@ def read_blocks(data):
     while p < len(buf):
         ncols, p = _varuint(buf, p)
         rows, p = _varuint(buf, p)
+        if ncols > len(buf) - p or (ncols and rows > len(buf) - p):      # every column / value takes at least one byte
+            raise ValueError("Native block header claims %d columns x %d rows in %d bytes" % (ncols, rows, len(buf) - p))
         cols, types = {}, {}
         for _ in range(ncols):
             name, p = _string(buf, p)
