@@ -178,6 +178,9 @@ func (r *gpuJobRunner) Close() { C.tad_shutdown(r.ctx) }
 // whose text is not a dotted quad (IPv6, empty): the caller gives those dictionary ids.  Returns the number of
 // bytes of buf the column occupied.
 func ipColumnFromNative(buf []byte, rows int) (ips []uint32, isV4 []bool, used int, err error) {
+	if rows == 0 || len(buf) == 0 {
+		return nil, nil, 0, nil
+	}
 	offsets := make([]uint64, rows)
 	lengths := make([]uint32, rows)
 	var n C.size_t
