@@ -221,6 +221,13 @@ int tad_ch_parse_ipv4(const uint8_t *buf, const uint64_t *offsets, const uint32_
  * Needs at most 16 bytes per row; TAD_ERR_INVALID_ARG if out_cap is too small. */
 int tad_ch_format_ipv4(const uint32_t *ips, uint64_t rows, uint8_t *out, size_t out_cap, size_t *written);
 
+/* Dense dictionary ids (order of first appearance) for a String column: ids[i] in [0, *n_unique); first_row[k] is the
+ * row at which id k first occurs (the caller reads the k-th name from there).  first_row needs room for `rows` entries.
+ * This is how pod namespaces / labels / service-port names become the u32 key columns of the aggregated-flow modes
+ * (anomaly_detection.py:511-609) and the namespace ids of the ignore list (:576-580). */
+int tad_ch_dictionary(const uint8_t *buf, const uint64_t *offsets, const uint32_t *lengths, uint64_t rows, uint32_t *ids,
+                      uint64_t *first_row, uint32_t *n_unique);
+
 #ifdef __cplusplus
 }
 #endif

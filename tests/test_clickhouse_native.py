@@ -209,3 +209,17 @@ def test_mutated_streams_never_crash_the_decoder():
             pass
 
     run()
+
+
+def test_dictionary_matches_a_python_dict_on_many_values():
+    rng = np.random.default_rng(11)
+    vocab = ["ns-%d" % i for i in range(5000)] + ["", "x" * 300, "é"]
+    vals = [vocab[i] for i in rng.integers(0, len(vocab), 60000)]
+    (cols, _t, _r), = list(chn.read_blocks(chn.write_native([("ns", "String", vals)])))
+    ids, names = cols["ns"].codes()
+    want, order = {}, []
+    for v in vals:
+        if v not in want:
+            want[v] = len(order)
+            order.append(v)
+    assert names == order and ids.tolist() == [want[v] for v in vals]

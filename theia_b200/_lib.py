@@ -20,7 +20,7 @@ TAD_REDUCE_MAX, TAD_REDUCE_SUM = 0, 1
 EXPORTS = ("tad_abi_version", "tad_strerror", "tad_init", "tad_shutdown", "tad_alloc_columns",
            "tad_free_columns", "tad_submit", "tad_poll", "tad_wait", "tad_result", "tad_cancel",
            "tad_release", "tad_get_unique_id", "tad_alloc_ns_columns", "tad_ch_string_index", "tad_ch_parse_ipv4",
-           "tad_ch_format_ipv4")
+           "tad_ch_format_ipv4", "tad_ch_dictionary")
 
 
 class TadConfig(C.Structure):
@@ -86,5 +86,6 @@ def load():
     L.tad_ch_string_index.argtypes = [C.c_void_p, C.c_size_t, C.c_uint64, C.c_void_p, C.c_void_p, C.POINTER(C.c_size_t)]
     L.tad_ch_parse_ipv4.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
     L.tad_ch_format_ipv4.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    L.tad_ch_dictionary.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)]
     _lib = L
     return L

@@ -73,13 +73,18 @@ class StringColumn:
         return out, ok.astype(bool)
 
     def codes(self):
-        """(ids, names): dense dictionary ids in order of first appearance -- the shim's per-job string dictionary."""
-        vals = self.to_numpy()
-        names, first, inv = np.unique(vals, return_index=True, return_inverse=True)
-        order = np.argsort(first, kind="stable")
-        rank = np.empty(len(order), dtype=np.uint32)
-        rank[order] = np.arange(len(order), dtype=np.uint32)
-        return rank[inv].astype(np.uint32), [str(x) for x in names[order]]
+        """(ids, names): dense dictionary ids in order of first appearance -- the shim's per-job string dictionary
+        (hashing and comparison run in the library; only the distinct names become Python strings)."""
+        n = len(self)
+        ids, first = np.zeros(n, dtype=np.uint32), np.zeros(max(n, 1), dtype=np.uint64)
+        nu = C.c_uint32(0)
+        if n:
+            base = np.frombuffer(self.buf, dtype=np.uint8)
+            rc = _lib.load().tad_ch_dictionary(base.ctypes.data, self.offsets.ctypes.data, self.lengths.ctypes.data, n,
+                                               ids.ctypes.data, first.ctypes.data, C.byref(nu))
+            if rc != 0:
+                raise ValueError("tad_ch_dictionary failed (%d)" % rc)
+        return ids, [self[int(r)] for r in first[:nu.value]]
 
 
 def _varuint(buf, p: int):

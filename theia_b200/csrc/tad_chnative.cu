@@ -101,4 +101,53 @@ int tad_ch_format_ipv4(const uint32_t *ips, uint64_t rows, uint8_t *out, size_t 
     return TAD_OK;
 }
 
+int tad_ch_dictionary(const uint8_t *buf, const uint64_t *offsets, const uint32_t *lengths, uint64_t rows, uint32_t *ids,
+                      uint64_t *first_row, uint32_t *n_unique)
+{
+    if ((!buf && rows) || !offsets || !lengths || !ids || !first_row || !n_unique) return TAD_ERR_INVALID_ARG;
+    if (rows >= (1ull << 32)) return TAD_ERR_INVALID_ARG;
+    // open addressing over (hash, id); the table doubles when half full.  FNV-1a over the value bytes.
+    size_t cap = 1024;
+    std::vector<uint32_t> slot_id(cap, 0xffffffffu);
+    std::vector<uint64_t> slot_hash(cap, 0);
+    uint32_t n = 0;
+    for (uint64_t i = 0; i < rows; i++) {
+        const uint8_t *s = buf + offsets[i];
+        const uint32_t len = lengths[i];
+        uint64_t h = 1469598103934665603ull;
+        for (uint32_t k = 0; k < len; k++) h = (h ^ s[k]) * 1099511628211ull;
+        h ^= h >> 29;
+        size_t p = (size_t)h & (cap - 1);
+        for (;;) {
+            const uint32_t id = slot_id[p];
+            if (id == 0xffffffffu) {                        // new value
+                slot_id[p] = n;
+                slot_hash[p] = h;
+                first_row[n] = i;
+                ids[i] = n++;
+                break;
+            }
+            const uint64_t r = first_row[id];
+            if (slot_hash[p] == h && lengths[r] == len && memcmp(buf + offsets[r], s, len) == 0) { ids[i] = id; break; }
+            p = (p + 1) & (cap - 1);
+        }
+        if ((size_t)n * 2 > cap) {                          // grow and re-insert (ids are stable)
+            cap *= 2;
+            std::vector<uint32_t> nid(cap, 0xffffffffu);
+            std::vector<uint64_t> nh(cap, 0);
+            for (size_t q = 0; q < slot_id.size(); q++) {
+                if (slot_id[q] == 0xffffffffu) continue;
+                size_t t = (size_t)slot_hash[q] & (cap - 1);
+                while (nid[t] != 0xffffffffu) t = (t + 1) & (cap - 1);
+                nid[t] = slot_id[q];
+                nh[t] = slot_hash[q];
+            }
+            slot_id.swap(nid);
+            slot_hash.swap(nh);
+        }
+    }
+    *n_unique = n;
+    return TAD_OK;
+}
+
 }  // extern "C"
