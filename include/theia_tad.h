@@ -206,7 +206,7 @@ int tad_get_unique_id(void *out, size_t bytes);
  * The reference job moves rows over JDBC (read: anomaly_detection.py:655-662; write: :713-726).  The shim streams
  * `SELECT ... FORMAT Native` column blocks instead (clickhouse-go, go.mod:7) and copies every fixed-width column
  * (UInt8/16/64, DateTime = UInt32; create_table.sh:31-85) straight into the tad_columns buffers.  Only String
- * columns need work: these three calls index them, turn IPv4 text into the u32 key column and back.
+ * columns need work: these calls index them, turn IPv4 text into the u32 key column and back, and dictionary-encode the rest.
  * theia_b200/clickhouse_native.py is the block reader / writer built on them. */
 
 /* A String column of `rows` values is rows x (VarUInt length, bytes).  Writes the payload position and length of
