@@ -1,0 +1,91 @@
+"""The job's entry point (theia_b200.anomaly_detection.main) as a drop-in for ``python anomaly_detection.py <argv>``:
+same options, ClickHouse over the HTTP port of --db_jdbc_url, results appended to default.tadetector."""
+import http.server
+import threading
+import urllib.parse
+
+import numpy as np
+
+from theia_b200 import anomaly_detection as ad
+from theia_b200 import clickhouse_native as chn
+
+from .test_clickhouse_native import _RecordingEngine, _flows_as_native, _named_flows
+
+
+class _FakeTransport:
+    def __init__(self, stream: bytes):
+        self.stream, self.selects, self.inserts = stream, [], []
+
+    def select_native(self, sql):
+        self.selects.append(sql)
+        return self.stream
+
+    def insert_native(self, table, block):
+        self.inserts.append((table, block))
+
+
+def test_main_reads_flows_and_appends_to_tadetector():
+    flows = _named_flows(seed=21, series=8, points=6)
+    tr, eng = _FakeTransport(_flows_as_native(flows, block_rows=20)), _RecordingEngine()
+    rc = ad.main(["--algo", "EWMA", "--id", "abc", "--start_time", "2020-01-01 00:00:00", "--ns-ignore-list", '["kube-system"]'],
+                 engine=eng, transport=tr)
+    assert rc == 0
+    assert tr.selects == ["SELECT flowEndSeconds, throughput, sourceIP, sourceTransportPort, destinationIP, "
+                          "destinationTransportPort, protocolIdentifier, flowStartSeconds, sourcePodNamespace, "
+                          "destinationPodNamespace FROM default.flows WHERE flowStartSeconds >= '2020-01-01 00:00:00'"]
+    table, kw = eng.calls[0]
+    assert kw["algo"] == "EWMA" and kw["tad_id"] == "abc" and kw["start_time"] > 0 and len(kw["ns_ignore"]) == 1
+    assert np.array_equal(table["value"], np.asarray(flows["throughput"]))
+    (name, body), = tr.inserts
+    got = chn.read_native(body)
+    assert name == "default.tadetector" and got["anomaly"].tolist() == ["NO ANOMALY DETECTED"] and got["id"].tolist() == ["abc"]
+    assert got["algoType"].tolist() == ["EWMA"] and got["aggType"].tolist() == ["None"]
+
+
+def test_main_generates_an_id_and_handles_an_empty_table():
+    tr, eng = _FakeTransport(b""), _RecordingEngine()
+    assert ad.main(["--algo", "DBSCAN", "--agg-flow", "svc"], engine=eng, transport=tr) == 0
+    assert tr.selects == ["SELECT flowEndSeconds, throughput, destinationServicePortName FROM default.flows"]
+    got = chn.read_native(tr.inserts[0][1])
+    assert len(got["id"][0]) == 36 and got["aggType"].tolist() == ["svc"] and got["algoType"].tolist() == ["DBSCAN"]
+
+
+def test_bad_options_exit_like_the_reference():
+    assert ad.main(["--no-such-option"], engine=_RecordingEngine(), transport=_FakeTransport(b"")) == 2
+    try:
+        ad.main(["--algo", "KMEANS"], engine=_RecordingEngine(), transport=_FakeTransport(b""))
+    except SystemExit as e:
+        assert e.code == 2
+    else:
+        raise AssertionError("invalid --algo must exit 2")
+
+
+def test_clickhouse_http_speaks_to_the_port_of_the_jdbc_url():
+    seen = []
+
+    class H(http.server.BaseHTTPRequestHandler):
+        def do_POST(self):
+            body = self.rfile.read(int(self.headers.get("Content-Length", 0)))
+            q = urllib.parse.parse_qs(urllib.parse.urlparse(self.path).query)
+            seen.append((q, self.headers.get("X-ClickHouse-User"), self.headers.get("X-ClickHouse-Key"), body))
+            out = b"NATIVE" if q["query"][0].startswith("SELECT") else b""
+            self.send_response(200)
+            self.send_header("Content-Length", str(len(out)))
+            self.end_headers()
+            self.wfile.write(out)
+
+        def log_message(self, *a):
+            pass
+
+    srv = http.server.HTTPServer(("127.0.0.1", 0), H)
+    th = threading.Thread(target=srv.serve_forever, daemon=True)
+    th.start()
+    try:
+        ch = ad.ClickHouseHTTP("jdbc:clickhouse://127.0.0.1:%d/default" % srv.server_address[1], user="u", password="p")
+        assert ch.select_native("SELECT 1 ") == b"NATIVE"
+        ch.insert_native("default.tadetector", b"\\x01\\x02")
+    finally:
+        srv.shutdown()
+    (q1, u1, k1, b1), (q2, u2, k2, b2) = seen
+    assert q1 == {"query": ["SELECT 1 FORMAT Native"], "database": ["default"]} and (u1, k1, b1) == ("u", "p", b"")
+    assert q2["query"] == ["INSERT INTO default.tadetector FORMAT Native"] and b2 == b"\\x01\\x02"

@@ -11,8 +11,11 @@ anomaly_detection (:647-710)            anomaly_detection(): plan -> host string
                                         encoding -> tad_submit / tad_wait / tad_result -> tadetector rows
 filter_df_with_true_anomalies (:352-421) _result_rows(): per-aggregation column sets + the sentinel row
 remove_meaningless_labels (:631-644)    remove_meaningless_labels()
-main()/getopt (:729-900)                parse_args(): same long options (and the controller's spelling
-                                        --ns-ignore-list, which the reference's getopt rejects)
+main()/getopt (:729-900)                main() / parse_args(): same long options (and the controller's spelling
+                                        --ns-ignore-list, which the reference's getopt rejects), same
+                                        CH_USERNAME / CH_PASSWORD, same tables; ClickHouse is reached over the
+                                        HTTP port of --db_jdbc_url with FORMAT Native (ClickHouseHTTP)
+write_anomaly_detection_result (:713-726) clickhouse_native.tadetector_block() -> INSERT ... FORMAT Native
 
 Flow tables are dicts of numpy arrays named like the ClickHouse ``flows`` columns
 (build/charts/theia/provisioning/datasources/create_table.sh:31-85); IPs may be dotted strings or u32.
@@ -23,7 +26,11 @@ from __future__ import annotations
 import calendar
 import getopt
 import json
+import logging
+import os
+import sys
 import time
+import uuid
 from dataclasses import dataclass, field
 from datetime import datetime
 
@@ -32,6 +39,8 @@ import numpy as np
 from . import _lib as L
 
 TABLE_NAME = "default.flows"
+RESULT_TABLE_NAME = "default.tadetector"                                               # anomaly_detection.py:732
+DEFAULT_JDBC_URL = "jdbc:clickhouse://clickhouse-clickhouse.flow-visibility.svc:8123"   # anomaly_detection.py:730-731
 MEANINGLESS_LABELS = ("pod-template-hash", "controller-revision-hash", "pod-template-generation")
 VALID_ALGOS = ("EWMA", "ARIMA", "DBSCAN")
 KEY_SLOTS = ("src_ip", "src_port", "dst_ip", "dst_port", "proto", "flow_start")
@@ -316,7 +325,7 @@ def parse_args(argv):
     opts, _ = getopt.getopt(argv, "ht:d:s:e:i:n:f:l:x:p:N:P:", [
         "help", "algo=", "db_jdbc_url=", "start_time=", "end_time=", "id=", "ns_ignore_list=", "ns-ignore-list=",
         "agg-flow=", "pod-label=", "external-ip=", "svc-port-name=", "pod-name=", "pod-namespace="])
-    out = {"algo": "", "start_time": "", "end_time": "", "id": None, "ns_ignore_list": [], "agg_flow": "",
+    out = {"algo": "", "db_jdbc_url": DEFAULT_JDBC_URL, "start_time": "", "end_time": "", "id": None, "ns_ignore_list": [], "agg_flow": "",
            "pod_label": "", "external_ip": "", "svc_port_name": "", "pod_name": "", "pod_namespace": ""}
     for opt, arg in opts:
         if opt in ("-a", "--algo"):
@@ -336,6 +345,8 @@ def parse_args(argv):
             out["ns_ignore_list"] = lst
         elif opt in ("-i", "--id"):
             out["id"] = arg
+        elif opt in ("-d", "--db_jdbc_url"):
+            out["db_jdbc_url"] = arg
         elif opt in ("-f", "--agg-flow"):
             out["agg_flow"] = arg
         elif opt in ("-l", "--pod-label"):
@@ -356,3 +367,123 @@ def timed_job(engine, *args, **kw):
     t0 = time.time()
     rows, st = anomaly_detection(engine, *args, **kw)
     return rows, st, time.time() - t0
+
+
+# ------------------------------------------------------------------------------------------------
+# the job's entry point: same argv, same environment, same tables as the reference's main()
+# ------------------------------------------------------------------------------------------------
+logger = logging.getLogger("anomaly_detection")
+
+
+class ClickHouseHTTP:
+    """ClickHouse over its HTTP interface.  The reference hands its JDBC URL to the ClickHouse JDBC driver
+    (anomaly_detection.py:655-662, 720-726), which talks to that very HTTP port (8123 in the default URL, :730-731);
+    here the same host:port receives the query with ``FORMAT Native`` and the column blocks come back as bytes.
+    Credentials: CH_USERNAME / CH_PASSWORD from the environment, as the reference reads them (:659-660)."""
+
+    def __init__(self, jdbc_url: str = DEFAULT_JDBC_URL, user=None, password=None, timeout: float = 3600.0):
+        rest = jdbc_url
+        for prefix in ("jdbc:clickhouse://", "jdbc:ch://", "clickhouse://", "http://"):
+            if rest.startswith(prefix):
+                rest = rest[len(prefix):]
+                break
+        hostport, _, tail = rest.partition("/")
+        self.base = "http://" + hostport + "/"
+        self.database = tail.split("?")[0]
+        self.user = os.getenv("CH_USERNAME") if user is None else user
+        self.password = os.getenv("CH_PASSWORD") if password is None else password
+        self.timeout = timeout
+
+    def _post(self, query: str, body: bytes = b"") -> bytes:
+        import urllib.parse
+        import urllib.request
+        params = {"query": query}
+        if self.database:
+            params["database"] = self.database
+        req = urllib.request.Request(self.base + "?" + urllib.parse.urlencode(params), data=body, method="POST")
+        if self.user:
+            req.add_header("X-ClickHouse-User", self.user)
+        if self.password:
+            req.add_header("X-ClickHouse-Key", self.password)
+        with urllib.request.urlopen(req, timeout=self.timeout) as resp:
+            return resp.read()
+
+    def select_native(self, sql: str) -> bytes:
+        return self._post(sql.rstrip() + " FORMAT Native")
+
+    def insert_native(self, table: str, block: bytes) -> None:
+        self._post("INSERT INTO %s FORMAT Native" % table, block)
+
+
+def raw_select_sql(plan: QueryPlan, pod_label=None, pod_name=None, pod_namespace=None) -> str:
+    """The SELECT this job sends instead of generate_tad_sql_query's text: the raw ``flows`` columns the plan needs.
+    Grouping, max / sum, the namespace ignore list and the string predicates run here (GPU / host), so ClickHouse only
+    scans; the time window is still pushed down with the reference's own conditions (:581-586) to bound the transfer."""
+    cols = ["flowEndSeconds", "throughput"]
+    for br in plan.branches:
+        for src in br.key.values():
+            if isinstance(src, str) and src not in cols:
+                cols.append(src)
+    extra = []
+    if plan.agg_flow == "pod":
+        for side in ("source", "destination"):
+            extra += [side + "PodLabels"] + ([side + "PodName"] if pod_name else []) + \
+                     ([side + "PodNamespace"] if (pod_namespace and (pod_label or pod_name)) else [])
+    elif plan.agg_flow == "external":
+        extra += ["flowType", "destinationIP"]
+    elif plan.agg_flow == "svc":
+        extra += ["destinationServicePortName"]
+    if plan.ns_ignore:
+        extra += ["sourcePodNamespace", "destinationPodNamespace"]
+    for c in extra:
+        if c not in cols:
+            cols.append(c)
+    sql = "SELECT {} FROM {}".format(", ".join(cols), TABLE_NAME)
+    where = []
+    if plan.start_time:
+        where.append("flowStartSeconds >= '{}'".format(plan.start_time))
+    if plan.end_time:
+        where.append("flowEndSeconds < '{}'".format(plan.end_time))
+    return sql + (" WHERE " + " AND ".join(where) if where else "")
+
+
+def main(argv=None, engine=None, transport=None) -> int:
+    """Drop-in for ``python anomaly_detection.py <argv>`` (anomaly_detection.py:729-900): reads ``default.flows``,
+    writes ``default.tadetector``, logs the same completion line.  ``engine`` / ``transport`` are injection points for
+    the tests; in the job container they are the GPU engine and the ClickHouse HTTP endpoint of ``--db_jdbc_url``."""
+    from . import clickhouse_native as chn
+    try:
+        a = parse_args(sys.argv[1:] if argv is None else argv)
+    except getopt.GetoptError:
+        return 2                                                    # the reference exits 2 on bad options (:800-803)
+    t0 = time.time()
+    logger.info("Script started at {}".format(datetime.now().strftime("%a, %d %B %Y %H:%M:%S")))
+    if a["algo"] not in VALID_ALGOS:
+        raise ValueError("Algorithm should be in {}".format(" or ".join(VALID_ALGOS)))
+    own_engine = engine is None
+    if own_engine:
+        from .engine import TadEngine
+        engine = TadEngine(device=int(os.getenv("TAD_DEVICE", "0")))
+    transport = transport or ClickHouseHTTP(a["db_jdbc_url"])
+    try:
+        plan = plan_query(a["start_time"], a["end_time"], a["ns_ignore_list"], a["agg_flow"], a["pod_label"], a["external_ip"],
+                          a["svc_port_name"], a["pod_name"], a["pod_namespace"])
+        sql = raw_select_sql(plan, a["pod_label"], a["pod_name"], a["pod_namespace"])
+        flows = chn.flows_from_native(transport.select_native(sql))
+        for c in sql[len("SELECT "):sql.index(" FROM ")].split(", "):      # an empty table comes back as no block at all
+            flows.setdefault(c, np.zeros(0, dtype=np.uint64 if c == "throughput" else np.uint32))
+        tad_id = a["id"] or str(uuid.uuid4())                               # write_anomaly_detection_result (:715-718)
+        rows, _st = anomaly_detection(engine, a["algo"], flows, a["start_time"], a["end_time"], tad_id, a["ns_ignore_list"],
+                                      a["agg_flow"] or None, a["pod_label"] or None, a["external_ip"] or None,
+                                      a["svc_port_name"] or None, a["pod_name"] or None, a["pod_namespace"] or None)
+        transport.insert_native(RESULT_TABLE_NAME, chn.tadetector_block(rows))
+    finally:
+        if own_engine:
+            engine.close()
+    logger.info("Anomaly Detection completed, id: {}, in {} seconds ".format(tad_id, time.time() - t0))
+    return 0
+
+
+if __name__ == "__main__":
+    logging.basicConfig(level=logging.INFO)
+    sys.exit(main())
