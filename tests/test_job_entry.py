@@ -89,3 +89,29 @@ def test_clickhouse_http_speaks_to_the_port_of_the_jdbc_url():
     (q1, u1, k1, b1), (q2, u2, k2, b2) = seen
     assert q1 == {"query": ["SELECT 1 FORMAT Native"], "database": ["default"]} and (u1, k1, b1) == ("u", "p", b"")
     assert q2["query"] == ["INSERT INTO default.tadetector FORMAT Native"] and b2 == b"\\x01\\x02"
+
+
+def test_ipv6_addresses_group_like_text_and_come_back_as_text():
+    """Dual-stack tables: a column holding any non-IPv4 text is dictionary-encoded as a whole (ids and u32 addresses never
+    share a key column) and decoded through the same dictionary on the way out."""
+    n = 12
+    flows = {"sourceIP": np.array(["fd00::1", "10.0.0.1", "fd00::1"] * 4, dtype=object),
+             "destinationIP": np.array(["10.0.0.9"] * n, dtype=object),
+             "sourceTransportPort": np.full(n, 1000, np.uint16), "destinationTransportPort": np.full(n, 80, np.uint16),
+             "protocolIdentifier": np.full(n, 6, np.uint8), "flowStartSeconds": np.full(n, 100, np.uint32),
+             "flowEndSeconds": np.arange(200, 200 + n, dtype=np.uint32), "throughput": np.arange(1, n + 1, dtype=np.uint64)}
+    eng = _RecordingEngine()
+    ad.anomaly_detection(eng, "EWMA", flows, tad_id="t")
+    table, _ = eng.calls[0]
+    assert table["src_ip"].tolist() == [0, 1, 0] * 4                      # dictionary ids, first appearance
+    assert table["dst_ip"].tolist() == [(10 << 24) | 9] * n               # pure IPv4 column stays numeric
+    # decode: what the engine returns for series id 0 / address 10.0.0.9
+    plan = ad.plan_query()
+    dicts = {slot: ad.Dictionary() for slot in ad.KEY_SLOTS}
+    dicts["src_ip"].encode(flows["sourceIP"])
+    got = {"src_ip": np.array([0, 1]), "dst_ip": np.array([(10 << 24) | 9] * 2), "src_port": np.array([1000, 1000]),
+           "dst_port": np.array([80, 80]), "proto": np.array([6, 6]), "flow_start": np.array([100, 100]),
+           "flow_end": np.array([200, 201]), "stddev": np.array([1.0, 1.0]), "algo_calc": np.array([2.0, 2.0]),
+           "throughput": np.array([3.0, 3.0]), "anomaly": np.array([1, 1])}
+    rows = ad._result_rows(got, plan, dicts, "EWMA", "t", None)
+    assert [r["sourceIP"] for r in rows] == ["fd00::1", "10.0.0.1"] and rows[0]["destinationIP"] == "10.0.0.9"

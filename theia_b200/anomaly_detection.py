@@ -178,8 +178,23 @@ def ip_to_u32(col) -> np.ndarray:
     out = np.empty(len(a), dtype=np.uint32)
     for i, s in enumerate(a):
         p = str(s).split(".")
+        if len(p) != 4:
+            raise ValueError("not an IPv4 address: %r" % (s,))
         out[i] = (int(p[0]) << 24) | (int(p[1]) << 16) | (int(p[2]) << 8) | int(p[3])
     return out
+
+
+def encode_ip_column(col, dictionary: "Dictionary") -> np.ndarray:
+    """Key column for sourceIP / destinationIP.  IPv4 text becomes its u32 value; a column that holds anything else
+    (IPv6, as dual-stack clusters export it) is dictionary-encoded as a whole, so ids and addresses never mix in one
+    key column -- the reference groups by the text, and any injective encoding groups identically."""
+    a = np.asarray(col)
+    if a.dtype.kind in "iu":
+        return a.astype(np.uint32)
+    try:
+        return ip_to_u32(a)
+    except ValueError:
+        return dictionary.encode(a)
 
 
 def u32_to_ip(v: int) -> str:
@@ -223,7 +238,14 @@ def _host_mask(flows: dict, plan: QueryPlan, branch: Branch, pod_label, pod_name
     elif plan.agg_flow == "external":
         m &= np.asarray(flows["flowType"]) == 3
         if external_ip:
-            m &= ip_to_u32(flows["destinationIP"]) == ip_to_u32([external_ip])[0]
+            dst = np.asarray(flows["destinationIP"])
+            if dst.dtype.kind in "iu":                                # already the u32 key column (Native transport)
+                try:
+                    m &= dst == ip_to_u32([external_ip])[0]
+                except ValueError:
+                    m &= False                                        # an IPv6 literal never equals an IPv4 column
+            else:
+                m &= dst.astype(str) == external_ip                   # destinationIP = '...' (:590-592)
     elif plan.agg_flow == "svc":
         svc = np.asarray(flows["destinationServicePortName"]).astype(str)
         m &= (svc == svc_port_name) if svc_port_name else (svc != "")
@@ -255,7 +277,7 @@ def anomaly_detection(engine, algo_type: str, flows: dict, start_time: str = "",
             else:
                 raw = np.asarray(flows[src])[idx]
                 if src in ("sourceIP", "destinationIP"):
-                    cols[slot] = ip_to_u32(raw)
+                    cols[slot] = encode_ip_column(raw, dicts[slot])
                 elif raw.dtype.kind in "iu":
                     cols[slot] = raw
                 else:
@@ -278,6 +300,11 @@ def anomaly_detection(engine, algo_type: str, flows: dict, start_time: str = "",
     return _result_rows(got, plan, dicts, algo_type, tad_id, pod_label, now), st
 
 
+def _ip_text(dictionary: "Dictionary", v: int) -> str:
+    """Inverse of encode_ip_column: a column that went through the dictionary comes back through it."""
+    return dictionary.names[v] if dictionary.names else u32_to_ip(v)
+
+
 def _result_rows(got: dict, plan: QueryPlan, dicts: dict, algo_type: str, tad_id: str, pod_label, now=None) -> list:
     """filter_df_with_true_anomalies' projections (anomaly_detection.py:359-393), the string cast of ``anomaly``
     (:500-502), the ``id`` column (:503) and the sentinel row (:395-420)."""
@@ -297,12 +324,12 @@ def _result_rows(got: dict, plan: QueryPlan, dicts: dict, algo_type: str, tad_id
             else:
                 row["podName"] = second
         elif plan.agg_flow == "external":
-            row = {"destinationIP": u32_to_ip(int(got["dst_ip"][i]))}
+            row = {"destinationIP": _ip_text(dicts["dst_ip"], int(got["dst_ip"][i]))}
         elif plan.agg_flow == "svc":
             row = {"destinationServicePortName": dicts["src_ip"].names[int(got["src_ip"][i])]}
         else:
-            row = {"sourceIP": u32_to_ip(int(got["src_ip"][i])), "sourceTransportPort": int(got["src_port"][i]),
-                   "destinationIP": u32_to_ip(int(got["dst_ip"][i])),
+            row = {"sourceIP": _ip_text(dicts["src_ip"], int(got["src_ip"][i])), "sourceTransportPort": int(got["src_port"][i]),
+                   "destinationIP": _ip_text(dicts["dst_ip"], int(got["dst_ip"][i])),
                    "destinationTransportPort": int(got["dst_port"][i]), "protocolIdentifier": int(got["proto"][i]),
                    "flowStartSeconds": int(got["flow_start"][i])}
         row.update(common)
