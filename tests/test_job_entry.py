@@ -115,3 +115,37 @@ def test_ipv6_addresses_group_like_text_and_come_back_as_text():
            "throughput": np.array([3.0, 3.0]), "anomaly": np.array([1, 1])}
     rows = ad._result_rows(got, plan, dicts, "EWMA", "t", None)
     assert [r["sourceIP"] for r in rows] == ["fd00::1", "10.0.0.1"] and rows[0]["destinationIP"] == "10.0.0.9"
+
+
+def test_main_end_to_end_on_the_oracle_engine_matches_the_direct_call():
+    """argv -> SELECT ... FORMAT Native -> decode -> plan / masks / dictionaries -> engine -> tadetector block, against the
+    rows the in-memory call produces (engine double backed by the CPU oracle: no GPU, no ClickHouse)."""
+    from . import test_host_mirror as thm
+    from .test_host_mirror_on_oracle import OracleEngine
+    fl = thm._flows(seed=4)
+    types = dict(chn_types(fl))
+    stream = chn.write_native([(k, types[k], np.asarray(v).astype(np.uint32) if types[k] == "String" and np.asarray(v).dtype.kind in "iu" else v)
+                               for k, v in fl.items()])
+    for argv, kw in ((["--algo", "EWMA", "--id", "j1"], {}),
+                     (["--algo", "EWMA", "--id", "j2", "--agg-flow", "svc"], {"agg_flow": "svc"}),
+                     (["--algo", "DBSCAN", "--id", "j3", "--agg-flow", "pod", "--pod-label", "web"], {"agg_flow": "pod", "pod_label": "web"})):
+        tr = _FakeTransport(stream)
+        assert ad.main(argv, engine=OracleEngine(), transport=tr) == 0
+        want, _ = ad.anomaly_detection(OracleEngine(), argv[1], fl, tad_id=argv[3], **kw)
+        got = chn.read_native(tr.inserts[0][1])
+        assert len(want) == len(got["id"]) and len(want) > 1
+        keyf = lambda r: (str(r.get("sourceIP", "")), str(r.get("podNamespace", "")), str(r.get("podLabels", "")), str(r.get("direction", "")),
+                          str(r.get("destinationServicePortName", "")), int(r.get("sourceTransportPort", 0)), int(r["flowEndSeconds"]), float(r["algoCalc"]))
+        rows_got = [{c: got[c][i] for c in got} for i in range(len(got["id"]))]
+        assert sorted(map(keyf, want)) == sorted(map(keyf, rows_got))
+
+
+def chn_types(fl):
+    for k, v in fl.items():
+        a = np.asarray(v)
+        if k in ("sourceIP", "destinationIP") or a.dtype.kind in "OUS":
+            yield k, "String"
+        elif k in ("flowStartSeconds", "flowEndSeconds"):
+            yield k, "DateTime"
+        else:
+            yield k, {1: "UInt8", 2: "UInt16", 4: "UInt32", 8: "UInt64"}[a.dtype.itemsize]
