@@ -26,7 +26,8 @@ class OracleEngine:
         if ns_ignore:
             keep &= ~np.isin(t["src_ns"], list(ns_ignore)) & ~np.isin(t["dst_ns"], list(ns_ignore))
         res = o.run_job(t, spec)
-        return dict(res.cols), {"rows_kept": int(keep.sum()), "state": "COMPLETED"}
+        return dict(res.cols), {"rows_kept": int(keep.sum()), "state": "COMPLETED", "completed_stages": 6, "total_stages": 6,
+                                "err_msg": ""}
 
 
 def test_agg_modes_on_the_oracle_engine():
@@ -39,6 +40,10 @@ def test_per_connection_with_namespace_ignore_and_window_on_the_oracle_engine():
 
 def test_sentinel_row_on_the_oracle_engine():
     thm.test_sentinel_row_when_nothing_is_anomalous(OracleEngine())
+
+
+def test_controller_state_machine_on_the_oracle_engine():
+    thm.test_controller_state_machine(OracleEngine())
 
 
 def test_reducer_codes_match():
