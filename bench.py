@@ -130,6 +130,29 @@ def python_port_rate(points):
         return {"unavailable": repr(e)[:120]}
 
 
+def native_decode_rate():
+    """Host-side rate of the ClickHouse Native-format ingest (theia_b200/clickhouse_native.py): 1e6 flow rows of the eight
+    engine columns, IPs as text.  A side figure for the transport that replaces JDBC; never fatal."""
+    try:
+        from theia_b200 import clickhouse_native as chn
+        from theia_b200 import synth
+        t = synth.make_flows(10_000, 100, seed=2)
+        cols = [("sourceIP", "String", t["src_ip"]), ("destinationIP", "String", t["dst_ip"]),
+                ("sourceTransportPort", "UInt16", t["src_port"]), ("destinationTransportPort", "UInt16", t["dst_port"]),
+                ("protocolIdentifier", "UInt8", t["proto"]), ("flowStartSeconds", "DateTime", t["flow_start"]),
+                ("flowEndSeconds", "DateTime", t["flow_end"]), ("throughput", "UInt64", t["value"])]
+        n = len(t["value"])
+        stream = b"".join(chn.write_native([(k, ty, v[lo:lo + 65536]) for k, ty, v in cols]) for lo in range(0, n, 65536))
+        chn.flows_from_native(stream)
+        t0 = time.perf_counter()
+        chn.flows_from_native(stream)
+        dt = time.perf_counter() - t0
+        return {"value": n / dt, "unit": "records/s", "bytes_per_record": len(stream) / n,
+                "sample": "%d rows in 64 Ki-row blocks, IPv4 addresses as text" % n}
+    except Exception as e:
+        return {"unavailable": repr(e)[:120]}
+
+
 def run_reference(args):
     """CPU arm: the oracle port with all host threads on a bounded sample of the same workload."""
     import numpy as np
@@ -343,6 +366,7 @@ def run_ours(args):
             line["cpu_baseline"] = {"value": len(t["value"]) / dt, "unit": "records/s", "cores": cores, "kind": "port",
                                     "sample": "%d rows x %d reps, oracle/tad_oracle.c OpenMP" % (len(t["value"]), reps),
                                     "python_port_1core": python_port_rate(n)}
+            line["native_ingest"] = native_decode_rate()
         print(json.dumps(line))
     hcols.free()
     eng.close()

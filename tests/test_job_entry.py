@@ -149,3 +149,35 @@ def chn_types(fl):
             yield k, "DateTime"
         else:
             yield k, {1: "UInt8", 2: "UInt16", 4: "UInt32", 8: "UInt64"}[a.dtype.itemsize]
+
+
+def test_ipv4_pushdown_selects_numeric_addresses_and_falls_back_to_text(monkeypatch):
+    plan = ad.plan_query()
+    sql = ad.raw_select_sql(plan, ipv4_pushdown=True)
+    assert "IPv4StringToNum(sourceIP) AS sourceIP" in sql and "IPv4StringToNum(destinationIP) AS destinationIP" in sql
+    flows = _named_flows(seed=2, series=4, points=5)
+    numeric = chn.write_native([("sourceIP", "UInt32", flows["sourceIP"]), ("destinationIP", "UInt32", flows["destinationIP"])]
+                               + [(k, t, flows[k]) for k, t in (("sourceTransportPort", "UInt16"), ("destinationTransportPort", "UInt16"),
+                                  ("protocolIdentifier", "UInt8"), ("flowStartSeconds", "DateTime"), ("flowEndSeconds", "DateTime"),
+                                  ("throughput", "UInt64"))])
+    text = _flows_as_native(flows, block_rows=1000)
+
+    class T(_FakeTransport):
+        def select_native(self, q):
+            self.selects.append(q)
+            if "IPv4StringToNum" in q and self.fail_pushdown:
+                raise RuntimeError("Code: 441. DB::Exception: Invalid IPv4 value")
+            return numeric if "IPv4StringToNum" in q else text
+
+    monkeypatch.setenv("TAD_IPV4_PUSHDOWN", "1")
+    tables = []
+    for fail in (False, True):
+        tr, eng = T(b""), _RecordingEngine()
+        tr.fail_pushdown = fail
+        assert ad.main(["--algo", "EWMA", "--id", "p"], engine=eng, transport=tr) == 0
+        assert len(tr.selects) == (2 if fail else 1)
+        tables.append(eng.calls[0][0])
+    for k in tables[0]:
+        assert (tables[0][k] is None) == (tables[1][k] is None)
+        if tables[0][k] is not None:
+            assert np.array_equal(tables[0][k], tables[1][k]), k
