@@ -181,3 +181,15 @@ def test_ipv4_pushdown_selects_numeric_addresses_and_falls_back_to_text(monkeypa
         assert (tables[0][k] is None) == (tables[1][k] is None)
         if tables[0][k] is not None:
             assert np.array_equal(tables[0][k], tables[1][k]), k
+
+
+def test_column_wise_insert_body_is_byte_identical_to_the_row_wise_one():
+    from . import test_host_mirror as thm
+    from .test_host_mirror_on_oracle import OracleEngine
+    fl = thm._flows(seed=4)
+    for kw in ({}, {"agg_flow": "svc"}, {"agg_flow": "external"}, {"agg_flow": "pod", "pod_label": "web"},
+               {"agg_flow": "pod", "pod_name": "pod-3", "pod_namespace": "flow-visibility"}):
+        got, _st, plan, dicts = ad.run_engine(OracleEngine(), "EWMA", fl, tad_id="T", **kw)
+        rows = ad._result_rows(got, plan, dicts, "EWMA", "T", kw.get("pod_label"))
+        assert len(rows) > 1
+        assert chn.tadetector_block_from_result(got, plan, dicts, "EWMA", "T") == chn.tadetector_block(rows), kw

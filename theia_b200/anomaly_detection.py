@@ -257,6 +257,16 @@ def anomaly_detection(engine, algo_type: str, flows: dict, start_time: str = "",
                       pod_name=None, pod_namespace=None, now=None):
     """anomaly_detection.py:647-710 + write_anomaly_detection_result (:713-726): returns the list of row dicts the
     reference appends to default.tadetector (one sentinel row when nothing is anomalous) and the job status."""
+    got, st, plan, dicts = run_engine(engine, algo_type, flows, start_time, end_time, tad_id, ns_ignore_list, agg_flow, pod_label,
+                                      external_ip, svc_port_name, pod_name, pod_namespace)
+    return _result_rows(got, plan, dicts, algo_type, tad_id, pod_label, now), st
+
+
+def run_engine(engine, algo_type: str, flows: dict, start_time: str = "", end_time: str = "", tad_id: str = "",
+               ns_ignore_list=(), agg_flow=None, pod_label=None, external_ip=None, svc_port_name=None,
+               pod_name=None, pod_namespace=None):
+    """Everything of :func:`anomaly_detection` up to the engine's result arrays: (result SoA, status, plan, dictionaries).
+    The job entry point builds its INSERT body from these column-wise instead of materialising a dict per row."""
     if algo_type not in VALID_ALGOS:
         raise ValueError("Algorithm should be in {}".format(" or ".join(VALID_ALGOS)))      # :811-818
     plan = plan_query(start_time, end_time, ns_ignore_list, agg_flow, pod_label, external_ip, svc_port_name, pod_name,
@@ -297,7 +307,7 @@ def anomaly_detection(engine, algo_type: str, flows: dict, start_time: str = "",
     ignore_ids = [ns_dict.ids[n] for n in plan.ns_ignore if n in ns_dict.ids]
     got, st = engine.run(table, algo=algo_type, reducer=plan.reducer, start_time=_epoch(plan.start_time),
                          end_time=_epoch(plan.end_time), tad_id=tad_id, ns_ignore=ignore_ids)
-    return _result_rows(got, plan, dicts, algo_type, tad_id, pod_label, now), st
+    return got, st, plan, dicts
 
 
 def _ip_text(dictionary: "Dictionary", v: int) -> str:
@@ -514,10 +524,14 @@ def main(argv=None, engine=None, transport=None) -> int:
         for c in (x.split(" AS ")[-1] for x in sql[len("SELECT "):sql.index(" FROM ")].split(", ")):   # empty table: no block at all
             flows.setdefault(c, np.zeros(0, dtype=np.uint64 if c == "throughput" else np.uint32))
         tad_id = a["id"] or str(uuid.uuid4())                               # write_anomaly_detection_result (:715-718)
-        rows, _st = anomaly_detection(engine, a["algo"], flows, a["start_time"], a["end_time"], tad_id, a["ns_ignore_list"],
-                                      a["agg_flow"] or None, a["pod_label"] or None, a["external_ip"] or None,
-                                      a["svc_port_name"] or None, a["pod_name"] or None, a["pod_namespace"] or None)
-        transport.insert_native(RESULT_TABLE_NAME, chn.tadetector_block(rows))
+        got, _st, plan, dicts = run_engine(engine, a["algo"], flows, a["start_time"], a["end_time"], tad_id, a["ns_ignore_list"],
+                                           a["agg_flow"] or None, a["pod_label"] or None, a["external_ip"] or None,
+                                           a["svc_port_name"] or None, a["pod_name"] or None, a["pod_namespace"] or None)
+        if len(got["flow_end"]):                                           # column-wise: no Python object per result row
+            block = chn.tadetector_block_from_result(got, plan, dicts, a["algo"], tad_id)
+        else:                                                               # the NO ANOMALY DETECTED sentinel (:395-420)
+            block = chn.tadetector_block(_result_rows(got, plan, dicts, a["algo"], tad_id, a["pod_label"] or None))
+        transport.insert_native(RESULT_TABLE_NAME, block)
     finally:
         if own_engine:
             engine.close()

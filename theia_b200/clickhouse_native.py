@@ -292,3 +292,79 @@ def _as_int(v) -> int:
         from datetime import datetime
         return int(datetime.strptime(v, "%Y-%m-%d %H:%M:%S").timestamp())
     return int(v)
+
+
+def _string_column_bytes(values=None, const=None, rows=0, ids=None, names=None) -> bytes:
+    """Data bytes of a String column without a Python object per row: a constant repeated, or dictionary ids mapped to
+    their pre-encoded names."""
+    if const is not None:
+        return _enc_string(const) * rows
+    enc = np.empty(len(names), dtype=object)
+    for i, nm in enumerate(names):
+        enc[i] = _enc_string(nm)
+    return b"".join(enc[np.asarray(ids, dtype=np.int64)].tolist())
+
+
+def tadetector_block_from_result(got: dict, plan, dicts: dict, algo_type: str, tad_id: str) -> bytes:
+    """The same INSERT body as ``tadetector_block(_result_rows(...))`` (theia_b200/anomaly_detection.py), built column-wise
+    from the engine's result arrays: no per-row dicts, so a job with millions of anomalous points stays array-speed.  The
+    caller handles the empty result (sentinel row) through the row-wise path."""
+    from .anomaly_detection import remove_meaningless_labels
+    n = len(got["flow_end"])
+    agg_type = plan.agg_flow if plan.agg_flow else "None"
+    cols = {name: None for name, _ in TADETECTOR_SCHEMA}
+
+    def ip_col(slot):
+        d = dicts[slot]
+        if d.names:                                             # the column went through the dictionary (non-IPv4 text)
+            return ("ids", np.asarray(got[slot]), list(d.names))
+        return ("ipv4", np.ascontiguousarray(got[slot], dtype=np.uint32), None)
+
+    if plan.agg_flow == "pod":
+        cols["podNamespace"] = ("ids", np.asarray(got["src_ip"]), list(dicts["src_ip"].names))
+        second = list(dicts["dst_ip"].names)
+        if plan.branches[0].group[1] == "podLabels":
+            cols["podLabels"] = ("ids", np.asarray(got["dst_ip"]), [remove_meaningless_labels(x) for x in second])
+        else:
+            cols["podName"] = ("ids", np.asarray(got["dst_ip"]), second)
+        cols["direction"] = ("ids", (np.asarray(got["proto"]) != 0).astype(np.int64), ["inbound", "outbound"])
+    elif plan.agg_flow == "external":
+        cols["destinationIP"] = ip_col("dst_ip")
+    elif plan.agg_flow == "svc":
+        cols["destinationServicePortName"] = ("ids", np.asarray(got["src_ip"]), list(dicts["src_ip"].names))
+    else:
+        cols["sourceIP"], cols["destinationIP"] = ip_col("src_ip"), ip_col("dst_ip")
+        cols["sourceTransportPort"] = ("num", got["src_port"], None)
+        cols["destinationTransportPort"] = ("num", got["dst_port"], None)
+        cols["protocolIdentifier"] = ("num", got["proto"], None)
+        cols["flowStartSeconds"] = ("num", got["flow_start"], None)
+    cols["flowEndSeconds"] = ("num", got["flow_end"], None)
+    cols["throughputStandardDeviation"] = ("num", got["stddev"], None)
+    cols["algoCalc"] = ("num", got["algo_calc"], None)
+    cols["throughput"] = ("num", got["throughput"], None)
+    for name, v in (("aggType", agg_type), ("algoType", algo_type), ("anomaly", "true"), ("id", tad_id)):
+        cols[name] = ("const", v, None)
+
+    out = [_enc_varuint(len(TADETECTOR_SCHEMA)), _enc_varuint(n)]
+    for name, typ in TADETECTOR_SCHEMA:
+        out.append(_enc_string(name))
+        out.append(_enc_string(typ))
+        spec = cols[name]
+        if typ == "String":
+            if spec is None:
+                out.append(b"\x00" * n)                          # '' : the table default
+            elif spec[0] == "const":
+                out.append(_string_column_bytes(const=spec[1], rows=n))
+            elif spec[0] == "ipv4":
+                buf = np.empty(16 * n + 16, dtype=np.uint8)
+                used = C.c_size_t(0)
+                if _lib.load().tad_ch_format_ipv4(spec[1].ctypes.data, n, buf.ctypes.data, buf.size, C.byref(used)) != 0:
+                    raise ValueError("tad_ch_format_ipv4 failed")
+                out.append(buf[:used.value].tobytes())
+            else:
+                out.append(_string_column_bytes(ids=spec[1], names=spec[2]))
+        else:
+            vals = np.zeros(n) if spec is None else np.asarray(spec[1])
+            out.append(np.ascontiguousarray(vals, dtype=_FIXED[re.sub(r"\(.*\)$", "", typ)]).tobytes())
+    return b"".join(out)
+
