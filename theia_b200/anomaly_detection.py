@@ -208,15 +208,31 @@ class Dictionary:
         self.ids, self.names = {}, []
 
     def encode(self, col) -> np.ndarray:
-        out = np.empty(len(col), dtype=np.uint32)
-        for i, s in enumerate(col):
-            s = str(s)
-            j = self.ids.get(s)
+        """ids in order of first appearance; hash-based (pandas.factorize) so a 1e8-row column costs seconds, not minutes:
+        only the distinct values are touched by Python code."""
+        a = np.asarray(col)
+        if len(a) == 0:
+            return np.zeros(0, dtype=np.uint32)
+        try:
+            import pandas as pd
+            codes, uniques = pd.factorize(a.astype(object) if a.dtype.kind != "O" else a, sort=False, use_na_sentinel=False)
+        except (ImportError, TypeError):                     # no pandas (or one without use_na_sentinel): same result, row by row
+            seen, codes, uniques = {}, np.empty(len(a), dtype=np.int64), []
+            for i, s in enumerate(a):
+                j = seen.get(s)
+                if j is None:
+                    j = seen[s] = len(uniques)
+                    uniques.append(s)
+                codes[i] = j
+        remap = np.empty(len(uniques), dtype=np.uint32)
+        for k, u in enumerate(uniques):
+            u = str(u)
+            j = self.ids.get(u)
             if j is None:
-                j = self.ids[s] = len(self.names)
-                self.names.append(s)
-            out[i] = j
-        return out
+                j = self.ids[u] = len(self.names)
+                self.names.append(u)
+            remap[k] = j
+        return remap[codes]
 
 
 def _host_mask(flows: dict, plan: QueryPlan, branch: Branch, pod_label, pod_name, pod_namespace, external_ip,
