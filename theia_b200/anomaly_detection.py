@@ -175,12 +175,21 @@ def ip_to_u32(col) -> np.ndarray:
     a = np.asarray(col)
     if a.dtype.kind in "iu":
         return a.astype(np.uint32)
-    out = np.empty(len(a), dtype=np.uint32)
-    for i, s in enumerate(a):
-        p = str(s).split(".")
-        if len(p) != 4:
-            raise ValueError("not an IPv4 address: %r" % (s,))
-        out[i] = (int(p[0]) << 24) | (int(p[1]) << 16) | (int(p[2]) << 8) | int(p[3])
+    n = len(a)
+    out, ok = np.zeros(n, dtype=np.uint32), np.zeros(n, dtype=np.uint8)
+    if n == 0:
+        return out
+    try:
+        b = np.ascontiguousarray(a.astype("S"))            # fixed-width ASCII cells; non-ASCII text cannot be an IPv4 address
+    except UnicodeEncodeError:
+        raise ValueError("not an IPv4 address column")
+    w = b.dtype.itemsize
+    offsets = np.arange(n, dtype=np.uint64) * np.uint64(w)
+    lengths = np.char.str_len(b).astype(np.uint32)
+    rc = L.load().tad_ch_parse_ipv4(b.ctypes.data, offsets.ctypes.data, lengths.ctypes.data, n, out.ctypes.data, ok.ctypes.data)
+    if rc != 0 or not ok.all():
+        bad = a[int(np.argmin(ok))] if rc == 0 else "?"
+        raise ValueError("not an IPv4 address: %r" % (bad,))
     return out
 
 
