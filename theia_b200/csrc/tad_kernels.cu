@@ -400,7 +400,8 @@ struct GroupSmem {
     static constexpr int HT = 2 * CAP;
     alignas(128) unsigned char x[32 * CAP];   // rows (TMA destination); later ts | tout | vout
     uint32_t ht[HT];                          // claim: low16 = rep row + 1, high16 = count; later (count << 16) | series idx
-    uint16_t soff[HT];                        // first point of the slot's series inside the bucket
+    uint16_t soff[CAP];                       // first point of series k inside the bucket (indexed by the dense series index:
+                                              // half the size of a per-slot array, which is what lets five 1024-row CTAs share an SM)
     alignas(8) unsigned long long mbar;
     uint32_t warp_sums[32];
     uint32_t total;
@@ -587,7 +588,7 @@ __global__ void __launch_bounds__(NT) group_kernel(const SegDesc seg, SeriesEntr
                 const uint32_t so = ex & 0xffffu, k = ex >> 16, cnt = w >> 16, rep = (w & 0xffffu) - 1u;
                 const uint4 kk = x4[2 * rep];
                 const uint32_t pp = x4[2 * rep + 1].w;
-                s.soff[base + i] = (uint16_t)so;
+                s.soff[k] = (uint16_t)so;
                 s.ht[base + i] = (cnt << 16) | k;
                 // series entry, in place over the (already staged) bucket rows
                 uint4 *e4 = reinterpret_cast<uint4 *>(ent + k);
@@ -631,8 +632,8 @@ __global__ void __launch_bounds__(NT) group_kernel(const SegDesc seg, SeriesEntr
         myB[j] = 0;
         if (r < n) {
             const uint32_t slot = mySP[j] & 0xffffu;
-            const uint32_t w = s.ht[slot], so = s.soff[slot];
-            const uint32_t cnt = w >> 16, k = w & 0xffffu;
+            const uint32_t w = s.ht[slot];
+            const uint32_t cnt = w >> 16, k = w & 0xffffu, so = s.soff[k];
             const uint32_t lo = tmin[k], range = tmax[k] - lo;
             uint32_t bin = 0;
             if (range) {
@@ -683,7 +684,7 @@ __global__ void __launch_bounds__(NT) group_kernel(const SegDesc seg, SeriesEntr
             tout[pos] = t;
             vout[pos] = myV[j];
             if (VRANK) pslot[pos] = (uint16_t)slot;
-            mySP[j] = pos | ((pos > s.soff[slot] ? 1u : 0u) << 31);
+            mySP[j] = pos | ((pos > s.soff[s.ht[slot] & 0xffffu] ? 1u : 0u) << 31);
         }
     }
     __syncthreads();
@@ -705,7 +706,7 @@ __global__ void __launch_bounds__(NT) group_kernel(const SegDesc seg, SeriesEntr
             const uint32_t w = s.ht[sl];
             const uint32_t cnt = w >> 16;
             if (cnt < 2) continue;
-            const uint32_t so = s.soff[sl];
+            const uint32_t so = s.soff[w & 0xffffu];
             uint32_t wr = 0;
             for (uint32_t q = 1; q < cnt; q++) {
                 if (tout[so + q] == tout[so + wr]) {
@@ -734,7 +735,8 @@ __global__ void __launch_bounds__(NT) group_kernel(const SegDesc seg, SeriesEntr
         __syncthreads();
         for (uint32_t p = tid; p < n; p += NT) {
             const uint32_t slot = pslot[p];
-            const uint32_t so = s.soff[slot], cnt = s.ht[slot] >> 16, me = p - so;
+            const uint32_t hw = s.ht[slot];
+            const uint32_t so = s.soff[hw & 0xffffu], cnt = hw >> 16, me = p - so;
             if (me >= cnt) continue;                    // hole left by the duplicate reduce
             const unsigned long long v = vout[p];
             uint32_t rank = (v == ~0ull) ? me : count_lt_u64(vout, so, so + me, v + 1ull);
@@ -892,11 +894,13 @@ struct DetectSmem {
     double qcalc[kDetectQueue];
     uint32_t qmeta[kDetectQueue];                     // bit 31: flag, bits 30..16: owning thread, low 16: unused
     uint32_t qpos[kDetectQueue];                      // index of the point in csr_v / csr_t
+    uint32_t qt[kDetectQueue];                        // flowEndSeconds of the queued rows (filled before the column writes)
     unsigned long long ent_a[kDetectThreads], ent_b[kDetectThreads];
     double ent_sd[kDetectThreads];
     uint32_t ent_proto[kDetectThreads];
     alignas(8) unsigned long long mbar;
-    uint32_t span_lo, span_hi, qcount, base, b0;
+    uint32_t span_lo, span_hi, base, b0;
+    uint32_t wq[kDetectThreads / 32], wpre[kDetectThreads / 32];   // rows queued per warp, exclusive prefix
     uint32_t win[kBucketWindow + 1], woff[kBucketWindow + 1];
 };
 
@@ -912,7 +916,6 @@ __global__ void __launch_bounds__(NT) detect_ewma_kernel(const SeriesEntry *__re
     if (threadIdx.x == 0) {
         sm.span_lo = 0xffffffffu;
         sm.span_hi = 0u;
-        sm.qcount = 0u;
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&sm.mbar)), "r"(1));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -949,39 +952,66 @@ __global__ void __launch_bounds__(NT) detect_ewma_kernel(const SeriesEntry *__re
                          : "=r"(done) : "r"(smem_u32(&sm.mbar)), "r"(0) : "memory");
         }
     }
-    const uint64_t *v = staged ? reinterpret_cast<const uint64_t *>(sm.stage) + (e.off - lo_a) : csr_v + e.off;
     bool has_sd = false;
     double sd = 0.0;
     if (e.n) {
-        sd = series_stddev(v, e.n, has_sd);
+        // two call sites so that each is compiled for its address space (LDS from the stage, LDG otherwise)
+        sd = staged ? series_stddev(reinterpret_cast<const uint64_t *>(sm.stage) + (e.off - lo_a), e.n, has_sd)
+                    : series_stddev(csr_v + e.off, e.n, has_sd);
         sm.ent_a[threadIdx.x] = e.a; sm.ent_b[threadIdx.x] = e.b; sm.ent_proto[threadIdx.x] = e.proto;
         sm.ent_sd[threadIdx.x] = sd;
-        if (has_sd || emit_all) {
-            double prev = 0.0;
-            for_each_value(v, e.n, [&](uint64_t raw, uint32_t q) {
-                const double x = __ull2double_rn(raw);
-                prev = __dadd_rn(__dmul_rn(0.5, prev), __dmul_rn(0.5, x));
-                const bool flag = has_sd && (fabs(__dsub_rn(x, prev)) > sd);
-                if (flag || emit_all) {
-                    const uint32_t slot = atomicAdd(&sm.qcount, 1u);
-                    if (slot < (uint32_t)kDetectQueue) {
-                        sm.qcalc[slot] = prev;
-                        sm.qpos[slot] = e.off + q;
-                        sm.qmeta[slot] = (flag ? 0x80000000u : 0u) | (threadIdx.x << 16);
-                    } else {                                        // queue full: direct emission
-                        const uint32_t idx = atomicAdd(&stats[ST_OUTCOUNT], 1u);
-                        if (idx < out_cap) write_out(out, idx, e, csr_t[e.off + q], sd, prev, x, flag);
-                    }
-                }
-            });
+    }
+    // ---- EWMA + flag, warp-synchronous: every lane walks its own series, all lanes of a warp step together, so the
+    // queue slot of a flagged point comes from one ballot and a warp-uniform register counter (no shared-memory atomic on
+    // the per-step path).  Each warp owns a fixed region of the queue; what does not fit is emitted directly.
+    constexpr uint32_t kWarps = NT / 32, kWarpQueue = kDetectQueue / kWarps;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t wbase = warp * kWarpQueue;
+    const uint32_t n_act = (e.n && (has_sd || emit_all)) ? e.n : 0u;
+    const uint32_t n_max = __reduce_max_sync(0xffffffffu, n_act);
+    uint32_t wcount = 0;
+    double prev = 0.0;
+    for (uint32_t q = 0; q < n_max; q++) {
+        const bool act = q < n_act;
+        const unsigned long long raw = !act ? 0ull : (staged ? sm.stage[e.off - lo_a + q] : csr_v[e.off + q]);
+        const double x = __ull2double_rn(raw);
+        prev = __dadd_rn(__dmul_rn(0.5, prev), __dmul_rn(0.5, x));
+        const bool flag = act && has_sd && (fabs(__dsub_rn(x, prev)) > sd);
+        const bool push = act && (flag || emit_all);
+        const uint32_t mask = __ballot_sync(0xffffffffu, push);
+        if (mask == 0u) continue;
+        const uint32_t slot = wcount + (uint32_t)__popc(mask & ((1u << lane) - 1u));
+        wcount += (uint32_t)__popc(mask);
+        if (push) {
+            if (slot < kWarpQueue) {
+                sm.qcalc[wbase + slot] = prev;
+                sm.qpos[wbase + slot] = e.off + q;
+                sm.qmeta[wbase + slot] = (flag ? 0x80000000u : 0u) | (threadIdx.x << 16);
+            } else {                                            // region full: direct emission
+                const uint32_t idx = atomicAdd(&stats[ST_OUTCOUNT], 1u);
+                if (idx < out_cap) write_out(out, idx, e, csr_t[e.off + q], sd, prev, x, flag);
+            }
         }
     }
+    if (lane == 0) sm.wq[warp] = min(wcount, kWarpQueue);
     __syncthreads();
-    const uint32_t nq = min(sm.qcount, (uint32_t)kDetectQueue);
-    if (threadIdx.x == 0) sm.base = nq ? atomicAdd(&stats[ST_OUTCOUNT], nq) : 0u;
+    if (threadIdx.x == 0) {
+        uint32_t nq = 0;
+        for (uint32_t w = 0; w < kWarps; w++) { sm.wpre[w] = nq; nq += sm.wq[w]; }
+        sm.base = nq ? atomicAdd(&stats[ST_OUTCOUNT], nq) : 0u;
+    }
     __syncthreads();
-    for (uint32_t j = threadIdx.x; j < nq; j += NT) {
-        const uint32_t idx = sm.base + j;
+    // ---- cooperative emission.  First the flow_end of every queued row (independent global loads, nothing between
+    // them that could alias), then the eleven coalesced column writes.
+#pragma unroll 4
+    for (uint32_t j = threadIdx.x; j < kWarps * kWarpQueue; j += NT) {
+        const uint32_t w = j / kWarpQueue, k = j - w * kWarpQueue;
+        if (k < sm.wq[w]) sm.qt[j] = csr_t[sm.qpos[j]];
+    }
+    for (uint32_t j = threadIdx.x; j < kWarps * kWarpQueue; j += NT) {
+        const uint32_t w = j / kWarpQueue, k = j - w * kWarpQueue;
+        if (k >= sm.wq[w]) continue;
+        const uint32_t idx = sm.base + sm.wpre[w] + k;
         if (idx >= out_cap) continue;
         const uint32_t meta = sm.qmeta[j], pos = sm.qpos[j], owner = (meta >> 16) & 0x7fffu;
         const uint64_t ka = sm.ent_a[owner], kb = sm.ent_b[owner];
@@ -991,7 +1021,7 @@ __global__ void __launch_bounds__(NT) detect_ewma_kernel(const SeriesEntry *__re
         out.src_port[idx] = (uint16_t)(kb >> 16);
         out.dst_port[idx] = (uint16_t)kb;
         out.proto[idx] = (uint8_t)sm.ent_proto[owner];
-        out.flow_end[idx] = csr_t[pos];
+        out.flow_end[idx] = sm.qt[j];
         out.stddev[idx] = sm.ent_sd[owner];
         out.algo_calc[idx] = sm.qcalc[j];
         out.throughput[idx] = __ull2double_rn(staged ? sm.stage[pos - lo_a] : csr_v[pos]);
