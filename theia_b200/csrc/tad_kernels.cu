@@ -27,24 +27,36 @@ namespace tad {
 // ----------------------------------------------------------------------------------------
 // small PTX helpers
 // ----------------------------------------------------------------------------------------
-__device__ __forceinline__ uint4 ldg_stream128(const void *p)
+// L2 eviction policy of the partition's streams (EXPERIMENT, TAD_SCATTER_LOADPOL / TAD_SCATTER_STOREPOL = 0 normal,
+// 1 evict_first, 2 evict_last): the input is read once (evict_first keeps it from displacing anything), a bucket's
+// 128-byte line receives its four rows over ~0.5 M rows of other traffic (evict_last should keep the partially
+// written line in L2 until it is complete, so that DRAM sees whole lines instead of single sectors).
+__device__ __forceinline__ uint64_t make_policy(int kind)
+{
+    uint64_t p;
+    if (kind == 1) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    else if (kind == 2) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint4 ldg_stream128(const void *p, uint64_t pol)
 {
     uint4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(pol));
     return r;
 }
-__device__ __forceinline__ uint2 ldg_stream64(const void *p)
+__device__ __forceinline__ uint2 ldg_stream64(const void *p, uint64_t pol)
 {
     uint2 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;" : "=r"(r.x), "=r"(r.y) : "l"(p), "l"(pol));
     return r;
 }
 // one 32-byte row = one 256-bit store = one full DRAM sector per request (sm_100: STG.E.256)
-__device__ __forceinline__ void stg256(void *p, uint4 lo, uint4 hi)
+__device__ __forceinline__ void stg256(void *p, uint4 lo, uint4 hi, uint64_t pol)
 {
-    asm volatile("st.global.L1::no_allocate.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
-                 :: "l"(p), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w)
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8}, %9;"
+                 :: "l"(p), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w), "l"(pol)
                  : "memory");
 }
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
@@ -88,19 +100,20 @@ struct OptScatter {
     uint32_t ovf_cap;
     Row32 *ovf;
     uint32_t *ovf_count;
+    int load_pol, store_pol;  // L2 eviction policy kinds (make_policy)
 };
 
-__device__ __forceinline__ void place_row(const RowRegs &r, uint32_t bucket, uint32_t pos, Row32 *part, const OptScatter &o)
+__device__ __forceinline__ void place_row(const RowRegs &r, uint32_t bucket, uint32_t pos, Row32 *part, const OptScatter &o, uint64_t spol)
 {
     const uint4 lo = make_uint4((uint32_t)r.a, (uint32_t)(r.a >> 32), (uint32_t)r.b, (uint32_t)(r.b >> 32));
     const uint4 hi = make_uint4((uint32_t)r.value, (uint32_t)(r.value >> 32), r.t, r.proto);
     if (o.cap == 0) {
-        stg256(part + pos, lo, hi);
+        stg256(part + pos, lo, hi, spol);
     } else if (pos < o.cap) {
-        stg256(part + (size_t)bucket * o.cap + pos, lo, hi);
+        stg256(part + (size_t)bucket * o.cap + pos, lo, hi, spol);
     } else {
         const uint32_t k = atomicAdd(o.ovf_count, 1u);
-        if (k < o.ovf_cap) stg256(o.ovf + k, lo, hi);
+        if (k < o.ovf_cap) stg256(o.ovf + k, lo, hi, spol);
     }
 }
 
@@ -113,7 +126,7 @@ __device__ __forceinline__ uint32_t hash_tag(uint64_t h, int bshift)
 }
 
 template <bool SCATTER>
-__device__ __forceinline__ void emit_row(const RowRegs &r, int bshift, uint32_t *counters, Row32 *part, const OptScatter &o)
+__device__ __forceinline__ void emit_row(const RowRegs &r, int bshift, uint32_t *counters, Row32 *part, const OptScatter &o, uint64_t spol)
 {
     if (!r.keep) return;
     const uint64_t h = key_hash(r.a, r.b, r.proto);
@@ -121,7 +134,7 @@ __device__ __forceinline__ void emit_row(const RowRegs &r, int bshift, uint32_t 
     if (SCATTER) {
         RowRegs rt = r;
         rt.proto |= hash_tag(h, bshift) << 8;
-        place_row(rt, bucket, atomicAdd(&counters[bucket], 1u), part, o);
+        place_row(rt, bucket, atomicAdd(&counters[bucket], 1u), part, o, spol);
     } else {
         atomicAdd(&counters[bucket], 1u);
     }
@@ -149,6 +162,7 @@ __global__ void __launch_bounds__(256) partition_kernel(ColPtrs c, uint64_t R, R
 {
     const uint64_t ngroups = (R + 7) / 8;
     const bool need_end = SCATTER || f.end_time != 0;
+    const uint64_t lpol = make_policy(opt.load_pol), spol = make_policy(opt.store_pol);
     for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups;
          g += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t base = g * 8;
@@ -157,16 +171,16 @@ __global__ void __launch_bounds__(256) partition_kernel(ColPtrs c, uint64_t R, R
             uint4 sip0 = z, sip1 = z, dip0 = z, dip1 = z, fs0 = z, fs1 = z, fe0 = z, fe1 = z, sp = z, dp = z;
             uint4 v0 = z, v1 = z, v2 = z, v3 = z;
             uint2 pr = make_uint2(0, 0);
-            if (c.src_ip) { sip0 = ldg_stream128(c.src_ip + base); sip1 = ldg_stream128(c.src_ip + base + 4); }
-            if (c.dst_ip) { dip0 = ldg_stream128(c.dst_ip + base); dip1 = ldg_stream128(c.dst_ip + base + 4); }
-            if (c.flow_start) { fs0 = ldg_stream128(c.flow_start + base); fs1 = ldg_stream128(c.flow_start + base + 4); }
-            if (need_end) { fe0 = ldg_stream128(c.flow_end + base); fe1 = ldg_stream128(c.flow_end + base + 4); }
-            if (c.src_port) sp = ldg_stream128(c.src_port + base);
-            if (c.dst_port) dp = ldg_stream128(c.dst_port + base);
-            if (c.proto) pr = ldg_stream64(c.proto + base);
+            if (c.src_ip) { sip0 = ldg_stream128(c.src_ip + base, lpol); sip1 = ldg_stream128(c.src_ip + base + 4, lpol); }
+            if (c.dst_ip) { dip0 = ldg_stream128(c.dst_ip + base, lpol); dip1 = ldg_stream128(c.dst_ip + base + 4, lpol); }
+            if (c.flow_start) { fs0 = ldg_stream128(c.flow_start + base, lpol); fs1 = ldg_stream128(c.flow_start + base + 4, lpol); }
+            if (need_end) { fe0 = ldg_stream128(c.flow_end + base, lpol); fe1 = ldg_stream128(c.flow_end + base + 4, lpol); }
+            if (c.src_port) sp = ldg_stream128(c.src_port + base, lpol);
+            if (c.dst_port) dp = ldg_stream128(c.dst_port + base, lpol);
+            if (c.proto) pr = ldg_stream64(c.proto + base, lpol);
             if (SCATTER) {
-                v0 = ldg_stream128(c.value + base); v1 = ldg_stream128(c.value + base + 2);
-                v2 = ldg_stream128(c.value + base + 4); v3 = ldg_stream128(c.value + base + 6);
+                v0 = ldg_stream128(c.value + base, lpol); v1 = ldg_stream128(c.value + base + 2, lpol);
+                v2 = ldg_stream128(c.value + base + 4, lpol); v3 = ldg_stream128(c.value + base + 6, lpol);
             }
             const uint32_t sipv[8] = {sip0.x, sip0.y, sip0.z, sip0.w, sip1.x, sip1.y, sip1.z, sip1.w};
             const uint32_t dipv[8] = {dip0.x, dip0.y, dip0.z, dip0.w, dip1.x, dip1.y, dip1.z, dip1.w};
@@ -201,17 +215,17 @@ __global__ void __launch_bounds__(256) partition_kernel(ColPtrs c, uint64_t R, R
                 }
 #pragma unroll
                 for (int i = 0; i < 8; i++)
-                    if (r[i].keep) place_row(r[i], bkt[i], pos[i], part, opt);
+                    if (r[i].keep) place_row(r[i], bkt[i], pos[i], part, opt, spol);
             } else {
 #pragma unroll
-                for (int i = 0; i < 8; i++) emit_row<SCATTER>(r[i], bshift, counters, part, opt);
+                for (int i = 0; i < 8; i++) emit_row<SCATTER>(r[i], bshift, counters, part, opt, spol);
             }
         } else {
             const uint64_t end = base + 8 < R ? base + 8 : R;
             for (uint64_t i = base; i < end; i++) {
                 RowRegs r;
                 load_row_scalar(c, f, i, SCATTER, r);
-                emit_row<SCATTER>(r, bshift, counters, part, opt);
+                emit_row<SCATTER>(r, bshift, counters, part, opt, spol);
             }
         }
     }
@@ -1174,11 +1188,23 @@ static uint32_t partition_grid(uint64_t R)
     return (uint32_t)(want < cap ? (want ? want : 1) : cap);
 }
 
+// TAD_SCATTER_LOADPOL / TAD_SCATTER_STOREPOL: 0 = evict_normal (default), 1 = evict_first, 2 = evict_last
+static int partition_policy(int which)
+{
+    static int pol[2] = {-1, -1};
+    if (pol[0] < 0) {
+        const char *a = getenv("TAD_SCATTER_LOADPOL"), *b = getenv("TAD_SCATTER_STOREPOL");
+        pol[0] = a ? atoi(a) : 0;
+        pol[1] = b ? atoi(b) : 0;
+    }
+    return pol[which];
+}
+
 cudaError_t launch_hist(cudaStream_t st, const ColPtrs &c, uint64_t R, const RowFilter &f, int logB, uint32_t *hist)
 {
     if (R == 0) return cudaSuccess;
     const int bshift = 64 - logB;
-    const OptScatter none{0, 0, nullptr, nullptr};
+    const OptScatter none{0, 0, nullptr, nullptr, partition_policy(0), 0};
     if (cols_aligned16(c))
         partition_kernel<false, true><<<partition_grid(R), 256, 0, st>>>(c, R, f, bshift, hist, nullptr, none);
     else
@@ -1191,7 +1217,7 @@ cudaError_t launch_scatter(cudaStream_t st, const ColPtrs &c, uint64_t R, const 
 {
     if (R == 0) return cudaSuccess;
     const int bshift = 64 - logB;
-    const OptScatter opt{slot_cap, ovf_cap, ovf, ovf_count};
+    const OptScatter opt{slot_cap, ovf_cap, ovf, ovf_count, partition_policy(0), partition_policy(1)};
     if (cols_aligned16(c))
         partition_kernel<true, true><<<partition_grid(R), 256, 0, st>>>(c, R, f, bshift, cursor, part, opt);
     else
