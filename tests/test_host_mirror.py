@@ -159,6 +159,33 @@ def test_agg_modes(engine):
 
 
 @pytest.mark.gpu
+def test_agg_modes_with_time_window(engine):
+    """external / svc with --start_time / --end_time: flowStartSeconds is not part of their key, yet the reference's
+    WHERE clause filters on it (anomaly_detection.py:581-586)."""
+    fl = _flows(seed=9)
+    n = len(fl["throughput"])
+    fl["flowStartSeconds"] = (1660199000 + 60 * np.random.default_rng(1).integers(0, 40, n)).astype(np.uint32)
+    start, end = "2022-08-11 06:35:00", "2022-08-11 07:00:00"
+    lo, hi = job._epoch(start), job._epoch(end)
+    win = [i for i in range(n) if fl["flowStartSeconds"][i] >= lo and fl["flowEndSeconds"][i] < hi]
+    assert 0 < len(win) < n and (fl["flowStartSeconds"] < lo).any()
+    rows, st = job.anomaly_detection(engine, "EWMA", fl, start_time=start, end_time=end, tad_id="w1", agg_flow="svc")
+    exp = _expected(fl, [((fl["destinationServicePortName"][i],), i) for i in win if fl["destinationServicePortName"][i] != ""])
+    got = {((r["destinationServicePortName"],), r["flowEndSeconds"], r["algoCalc"]) for r in rows if r["anomaly"] == "true"}
+    assert got == exp and len(exp) > 0
+    rows, st = job.anomaly_detection(engine, "EWMA", fl, start_time=start, end_time=end, tad_id="w2", agg_flow="external")
+    exp = _expected(fl, [((job.u32_to_ip(int(fl["destinationIP"][i])),), i) for i in win if fl["flowType"][i] == 3])
+    got = {((r["destinationIP"],), r["flowEndSeconds"], r["algoCalc"]) for r in rows if r["anomaly"] == "true"}
+    assert got == exp and len(exp) > 0
+    # start only: the lower bound alone must not empty the job either
+    rows, st = job.anomaly_detection(engine, "EWMA", fl, start_time=start, tad_id="w3", agg_flow="svc")
+    win2 = [i for i in range(n) if fl["flowStartSeconds"][i] >= lo]
+    exp = _expected(fl, [((fl["destinationServicePortName"][i],), i) for i in win2 if fl["destinationServicePortName"][i] != ""])
+    got = {((r["destinationServicePortName"],), r["flowEndSeconds"], r["algoCalc"]) for r in rows if r["anomaly"] == "true"}
+    assert got == exp and len(exp) > 0
+
+
+@pytest.mark.gpu
 def test_per_connection_with_namespace_ignore_and_window(engine):
     fl = _flows(seed=5)
     n = len(fl["throughput"])

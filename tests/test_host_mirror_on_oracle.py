@@ -34,6 +34,10 @@ def test_agg_modes_on_the_oracle_engine():
     thm.test_agg_modes(OracleEngine())
 
 
+def test_agg_modes_with_time_window_on_the_oracle_engine():
+    thm.test_agg_modes_with_time_window(OracleEngine())
+
+
 def test_per_connection_with_namespace_ignore_and_window_on_the_oracle_engine():
     thm.test_per_connection_with_namespace_ignore_and_window(OracleEngine())
 

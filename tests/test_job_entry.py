@@ -193,3 +193,26 @@ def test_column_wise_insert_body_is_byte_identical_to_the_row_wise_one():
         rows = ad._result_rows(got, plan, dicts, "EWMA", "T", kw.get("pod_label"))
         assert len(rows) > 1
         assert chn.tadetector_block_from_result(got, plan, dicts, "EWMA", "T") == chn.tadetector_block(rows), kw
+
+
+def test_main_svc_with_a_window_does_not_refilter_on_the_gpu():
+    """with --agg-flow svc / external the window's lower bound is a WHERE condition on a column that is not
+    part of the key; the SELECT pushes it down and the engine must not see start_time (its flow_start column is absent)."""
+    from . import test_host_mirror as thm
+    from .test_host_mirror_on_oracle import OracleEngine
+    fl = thm._flows(seed=4)
+    start = "2022-08-11 06:00:00"                     # every flowStartSeconds of the fixture is inside the window
+    assert (fl["flowStartSeconds"] >= ad._epoch(start)).all()
+    sel = {k: v for k, v in fl.items() if k in ("flowEndSeconds", "throughput", "destinationServicePortName")}
+    types = dict(chn_types(sel))
+    tr, eng = _FakeTransport(chn.write_native([(k, types[k], v) for k, v in sel.items()])), _RecordingEngine()
+    assert ad.main(["--algo", "EWMA", "--id", "w", "--agg-flow", "svc", "--start_time", start], engine=eng, transport=tr) == 0
+    assert tr.selects[0].endswith("WHERE flowStartSeconds >= '%s'" % start) and "flowStartSeconds" not in tr.selects[0].split(" FROM ")[0]
+    table, kw = eng.calls[0]
+    assert table["flow_start"] is None and kw["start_time"] == 0
+    # and the rows: same as without the window (it keeps everything here)
+    tr2 = _FakeTransport(tr.stream)
+    assert ad.main(["--algo", "EWMA", "--id", "w", "--agg-flow", "svc", "--start_time", start], engine=OracleEngine(), transport=tr2) == 0
+    want, _ = ad.anomaly_detection(OracleEngine(), "EWMA", fl, tad_id="w", agg_flow="svc")
+    got = chn.read_native(tr2.inserts[0][1])
+    assert len(got["id"]) == len(want) > 1

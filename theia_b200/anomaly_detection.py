@@ -274,6 +274,11 @@ def _host_mask(flows: dict, plan: QueryPlan, branch: Branch, pod_label, pod_name
     elif plan.agg_flow == "svc":
         svc = np.asarray(flows["destinationServicePortName"]).astype(str)
         m &= (svc == svc_port_name) if svc_port_name else (svc != "")
+    if plan.start_time and "flow_start" not in branch.key and flows.get("flowStartSeconds") is not None:
+        # external / svc: flowStartSeconds >= start is a WHERE condition (anomaly_detection.py:581-583) on a column
+        # that is not part of the key, so it cannot ride the engine's key column: filter here.  A table that does
+        # not carry the column came from raw_select_sql, whose WHERE clause already applied the same condition.
+        m &= np.asarray(flows["flowStartSeconds"]).astype(np.int64) >= _epoch(plan.start_time)
     return m
 
 
@@ -330,7 +335,12 @@ def run_engine(engine, algo_type: str, flows: dict, start_time: str = "", end_ti
         else:
             table[k] = np.concatenate([np.asarray(p[k]) for p in parts])
     ignore_ids = [ns_dict.ids[n] for n in plan.ns_ignore if n in ns_dict.ids]
-    got, st = engine.run(table, algo=algo_type, reducer=plan.reducer, start_time=_epoch(plan.start_time),
+    # The engine applies ``flowStartSeconds >= start`` to its flow_start KEY column.  In the external / svc modes
+    # flowStartSeconds is not a key (anomaly_detection.py:568-571), so the window's lower bound was applied above
+    # (_host_mask, or already by the WHERE clause of the SELECT the job entry sends) and must not reach the GPU, whose
+    # absent flow_start column reads as 0.
+    start = _epoch(plan.start_time) if table.get("flow_start") is not None else 0
+    got, st = engine.run(table, algo=algo_type, reducer=plan.reducer, start_time=start,
                          end_time=_epoch(plan.end_time), tad_id=tad_id, ns_ignore=ignore_ids)
     return got, st, plan, dicts
 

@@ -755,6 +755,12 @@ int validate(const tad_job_spec *spec, const tad_columns *cols, char *msg, size_
         snprintf(msg, n, "invalid request: flow_end and value columns are required");
         return TAD_ERR_INVALID_ARG;
     }
+    if (cols->rows && spec->start_time && !cols->flow_start) {
+        // flowStartSeconds >= start filters on the flow_start KEY column; a job whose key has none (the external / svc
+        // aggregated modes, anomaly_detection.py:568-571) applies that bound on the host, where the column lives
+        snprintf(msg, n, "invalid request: start_time needs the flow_start column");
+        return TAD_ERR_INVALID_ARG;
+    }
     if (cols->rows >= (1ull << 32) - 1) {
         snprintf(msg, n, "invalid request: at most 2^32-2 rows per GPU");
         return TAD_ERR_INVALID_ARG;
