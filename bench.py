@@ -25,6 +25,10 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# CPU arm: pin the OpenMP threads of the oracle port (one per hardware thread, no migration) before libgomp loads, so
+# that the baseline does not swing with the scheduler's mood from box to box
+os.environ.setdefault("OMP_PROC_BIND", "spread")
+os.environ.setdefault("OMP_PLACES", "threads")
 
 METRIC = "flow records/sec through EWMA anomaly detection"
 BYTES_PER_ROW = 29          # src_ip4 dst_ip4 src_port2 dst_port2 proto1 flow_start4 flow_end4 value8
@@ -112,6 +116,65 @@ def ncu_traffic(kernel, rows):
     return None
 
 
+K1, K2, K3, M32 = 2654435761, 2246822519, 3266489917, 0xffffffff
+
+
+def sample_mask(src_ip, dst_ip, frac):
+    """Same pseudo-random subset of connections on every rank, for torch (int64 bit patterns) and numpy (unsigned) columns:
+    a 20-bit hash of (sourceIP, destinationIP) below a threshold."""
+    try:
+        import torch
+        is_t = isinstance(src_ip, torch.Tensor)
+    except ImportError:
+        is_t = False
+    if is_t:
+        a, b = src_ip.to(torch.int64) & M32, dst_ip.to(torch.int64) & M32
+    else:
+        import numpy as np
+        a, b = src_ip.astype(np.uint64), dst_ip.astype(np.uint64)
+    h = ((a * K1) ^ (b * K2)) & M32
+    h = (h * K3) & M32
+    h = (h ^ (h >> 15)) & 0xfffff
+    return h < max(1, int(frac * (1 << 20)))
+
+
+def parity_check(eng, dcols, cols_t, algo, global_rows, total_series, dist, rank, world, want_connections=3000):
+    """One more (untimed) job on the bench table; the connections of a hash-selected sample are cross-checked bit for bit
+    against the CPU oracle (the checker; tests/test_gpu_full_size.py does the same): the input rows of the sample are
+    collected from every rank, the oracle runs stages A-E on them, and the result rows the engine produced for those
+    connections (on whichever rank owns them) must be identical in every column."""
+    import numpy as np
+    from oracle import c_oracle, tad_oracle
+    from theia_b200 import synth
+    frac = min(1.0, want_connections / max(1, total_series))
+    job = eng.submit(dcols, algo=algo, tad_id="parity", global_rows=global_rows)
+    job.wait()
+    res = job.result()
+    job.release()
+    m_in = sample_mask(cols_t["src_ip"], cols_t["dst_ip"], frac)
+    sub = synth.torch_cols_to_numpy(cols_t, m_in)
+    m_out = sample_mask(res["src_ip"], res["dst_ip"], frac)
+    got = {k: v[m_out] for k, v in res.items()}
+    if dist is not None:
+        box = [None] * world if rank == 0 else None
+        dist.gather_object((sub, got), box, dst=0)
+        if rank != 0:
+            return None
+        sub = {k: np.concatenate([b[0][k] for b in box]) for k in sub}
+        got = {k: np.concatenate([b[1][k] for b in box]) for k in got}
+    cols, ns, npts = c_oracle.run_job(sub, algo={"EWMA": 0, "ARIMA": 1, "DBSCAN": 2}[algo])
+    want, got = tad_oracle.canonicalize(cols), tad_oracle.canonicalize(got)
+    ok = len(want["flow_end"]) == len(got["flow_end"])
+    bad = []
+    if ok:
+        for c in want:
+            if not np.array_equal(want[c], got[c], equal_nan=True):
+                ok = False
+                bad.append(c)
+    return {"checked": int(ns), "input_rows": int(len(sub["value"])), "result_rows": int(len(want["flow_end"])),
+            "ok": bool(ok), "against": "oracle/tad_oracle.c, every result column bit-exact", **({"differs": bad} if bad else {})}
+
+
 def python_port_rate(points):
     """Single-core rate of the pure-Python restatement (numpy stages A/B + the per-series UDF loops the Spark workers
     would run, oracle/tad_oracle.py) on a 2e5-row sample: the 'local[1]'-style figure SURVEY section 8(d) asks for.
@@ -153,20 +216,43 @@ def native_decode_rate():
         return {"unavailable": repr(e)[:120]}
 
 
-def run_reference(args):
-    """CPU arm: the oracle port with all host threads on a bounded sample of the same workload."""
-    import numpy as np
-    from oracle import c_oracle
+def bench_table_numpy(series, points, seed=1):
+    """The bench table (BASELINE configs[1] shape) as numpy columns for the CPU arm: generated on the GPU when one is
+    visible (the numpy generator needs minutes for 1e8 rows), else with numpy.  Untimed."""
     from theia_b200 import synth
+    try:
+        import torch
+        if torch.cuda.is_available():
+            cols_t = synth.make_flows_torch(series, points, seed=seed, device=torch.device("cuda", 0))
+            t = synth.torch_cols_to_numpy(cols_t)
+            del cols_t
+            torch.cuda.empty_cache()
+            return t
+    except Exception:
+        pass
+    return synth.make_flows(series, points, seed=seed)
+
+
+def cpu_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def run_reference(args):
+    """CPU arm: the oracle port of the reference job (stages A-E) with all host threads, on the SAME table shape as our arm
+    (full size unless --ref-series bounds it)."""
+    from oracle import c_oracle
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    series = args.ref_series
-    t = synth.make_flows(series, args.points, seed=1)
+    cores = cpu_threads()
+    series = args.ref_series or args.series
+    t = bench_table_numpy(series, args.points)
     rows = len(t["value"])
     c_oracle.build()
-    for _ in range(args.warmup):
+    for _ in range(min(args.warmup, 1)):           # one warm-up pass is enough for a CPU job of seconds
         c_oracle.run_job(t, algo=0, threads=cores)
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -178,13 +264,89 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "EWMA, %d records / %d connections x %d points per GPU (BASELINE configs[1])" % (args.series * args.points, args.series, args.points),
-                   "sample": "each step runs the CPU path on a bounded sample: %d connections x %d points = %d rows" % (series, args.points, rows),
-                   "rows_per_step": rows},
-        "cpu_baseline": {"value": v, "unit": "records/s", "cores": cores, "kind": "port",
-                         "sample": "%d rows per step, oracle/tad_oracle.c with OpenMP on %d threads" % (rows, cores),
+                   "sample": "each step runs the CPU path on %d connections x %d points = %d rows%s" % (
+                       series, args.points, rows, "" if series == args.series else " (bounded sample)"),
+                   "rows_per_step": rows, "same_table_shape_as_ours": series == args.series},
+        "cpu_baseline": {"value": v, "unit": "records/s", "cores": cores, "threads_used": cores, "kind": "port",
+                         "omp": {k: os.environ.get(k) for k in ("OMP_PROC_BIND", "OMP_PLACES", "OMP_NUM_THREADS")},
+                         "sample": "%d rows per step, oracle/tad_oracle.c with OpenMP on %d threads; %d series, %d points found" % (
+                             rows, cores, ns, npts),
                          "python_port_1core": python_port_rate(args.points)},
         "e2e": {"value": v, "unit": "records/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
+
+
+def side_run(eng, dev, algo, series, points, steps, warmup, name):
+    """One of the other BASELINE configurations on this GPU: device-resident synthetic table, `warmup` + `steps` jobs, the
+    library's CUDA-event times, its own roofline figures and its own parity flag (sampled connections against the oracle;
+    ARIMA: against oracle/arima_oracle.py on a handful of connections, flags and relative error)."""
+    import torch
+    from theia_b200 import synth
+    from theia_b200.engine import DeviceColumns
+    out = {"config": name, "algo": algo}
+    try:
+        cols_t = synth.make_flows_torch(series, points, seed=5, device=dev, noisy=(algo == "ARIMA"))
+        rows = int(cols_t["value"].numel())
+        torch.cuda.synchronize()
+        dcols = DeviceColumns(rows, {k: v.data_ptr() for k, v in cols_t.items()})
+        dcols.keepalive = cols_t
+        ms, phase, launches, st = 0.0, {}, 0, None
+        for i in range(warmup + steps):
+            job = eng.submit(dcols, algo=algo, tad_id="side")
+            st = job.wait()
+            job.release()
+            if i >= warmup:
+                ms += st["device_ms"]
+                launches += st["gpu_launches"]
+                for k, v in st["phase_ms"].items():
+                    phase[k] = phase.get(k, 0.0) + v
+        ms /= steps
+        per = {k: v / steps for k, v in phase.items() if v}
+        peak, peak_src = peaks()
+        kern = {k: per[k] for k in ("hist", "scatter", "group", "detect") if per.get(k, 0) > 0}
+        dom = max(kern, key=kern.get)
+        out.update({"records": rows, "value": rows / (ms * 1e-3), "unit": "records/s", "ms_per_step": ms, "steps": steps,
+                    "warmup": warmup, "series": int(st["series"]), "series_per_s": int(st["series"]) / (ms * 1e-3),
+                    "result_rows": int(st["result_rows"]), "gpu_launches": launches, "phase_ms": per, "dtype": "f64",
+                    "roofline": {"bound": "hbm" if algo != "ARIMA" else "fp64 latency (compute bound: ~100 likelihood evaluations x t Kalman steps per fit)",
+                                 "kernel": dom, "achieved": BYTES_PER_ROW * rows / (kern[dom] * 1e-3) / 1e9, "peak": peak,
+                                 "unit": "GB/s", "frac": BYTES_PER_ROW * rows / (kern[dom] * 1e-3) / 1e9 / peak,
+                                 "pipeline_frac": BYTES_PER_ROW * rows / (ms * 1e-3) / 1e9 / peak, "traffic": None,
+                                 "peak_source": peak_src}})
+        if algo == "ARIMA":
+            out["fits_per_s"] = rows / (ms * 1e-3)            # one ARIMA(1,1,1) prefix fit per point (anomaly_detection.py:239-258)
+            out["parity"] = arima_parity(eng, cols_t, series)
+        else:
+            out["parity"] = parity_check(eng, dcols, cols_t, algo, 0, series, None, 0, 1)
+        del dcols, cols_t
+        torch.cuda.empty_cache()
+    except Exception as e:          # a side figure must not take the bench line down
+        out["unavailable"] = repr(e)[:200]
+    return out
+
+
+def arima_parity(eng, cols_t, series, want=3):
+    """ARIMA: a handful of connections against the SciPy restatement of statsmodels' fit (oracle/arima_oracle.py; the C
+    oracle has no ARIMA): share of identical flags, median / max relative error of algoCalc."""
+    try:
+        import numpy as np
+        from oracle import arima_oracle, tad_oracle
+        from theia_b200 import synth
+        m = sample_mask(cols_t["src_ip"], cols_t["dst_ip"], min(1.0, want / series))
+        sub = synth.torch_cols_to_numpy(cols_t, m)
+        got, _ = eng.run(sub, algo="ARIMA", tad_id="parity", emit_all=True)
+        res = tad_oracle.run_job(sub, tad_oracle.JobSpec(algo=tad_oracle.ALGO_ARIMA, emit_all=True),
+                                 arima_fn=arima_oracle.calculate_arima)
+        w, g = tad_oracle.canonicalize(dict(res.cols)), tad_oracle.canonicalize(got)
+        if len(w["flow_end"]) != len(g["flow_end"]) or not np.array_equal(w["flow_end"], g["flow_end"]):
+            return {"ok": False, "note": "different set of surviving series / points (%d vs %d rows)" % (len(g["flow_end"]), len(w["flow_end"]))}
+        rel = np.abs(g["algo_calc"] - w["algo_calc"]) / np.maximum(np.abs(w["algo_calc"]), 1e-300)
+        same = float(np.mean(g["anomaly"] == w["anomaly"]))
+        return {"checked": int(len(np.unique(sub["src_ip"]))), "points": int(len(rel)), "flags_identical": same,
+                "rel_err_median": float(np.median(rel)), "rel_err_max": float(rel.max()), "ok": bool(same >= 0.99),
+                "against": "oracle/arima_oracle.py (SciPy restatement; parity unpinned below ~1e-3, DESIGN.md section 8)"}
+    except Exception as e:
+        return {"ok": None, "unavailable": repr(e)[:160]}
 
 
 def run_ours(args):
@@ -225,8 +387,10 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    global_rows = rows * world if world > 1 else 0      # what the host's SELECT count() tells every rank (equal shards)
+
     def step(cols):
-        job = eng.submit(cols, algo=args.algo, tad_id="bench")
+        job = eng.submit(cols, algo=args.algo, tad_id="bench", global_rows=global_rows)
         st = job.wait()
         return job, st
 
@@ -258,12 +422,19 @@ def run_ours(args):
     if dist is not None:
         dist.all_reduce(tr)
     total_rows = int(tr[0])
+    assert world == 1 or total_rows == global_rows, "shards are not balanced"
+
+    # ---- parity: a sample of connections against the CPU oracle, at every N (untimed) -------------------------------
+    parity = None
+    if not args.no_parity:
+        parity = parity_check(eng, dcols, cols_t, args.algo, global_rows, S * world, dist, rank, world)
 
     # ---- e2e: host (pinned) buffers through the C ABI, H2D + D2H inside the timed region --------
     if args.no_e2e:
         if rank == 0:
-            print(json.dumps({"value": total_rows / (ms_dev * 1e-3), "ms_per_step": ms_dev,
-                              "phase_ms": {k: v / args.steps for k, v in phase.items()}, "note": "profiling run"}))
+            print(json.dumps({"value": total_rows / (ms_dev * 1e-3), "ms_per_step": ms_dev, "wall_ms_per_step": ms_wall,
+                              "phase_ms": {k: v / args.steps for k, v in phase.items()}, "parity": parity,
+                              "note": "profiling run"}))
         eng.close()
         if dist is not None:
             dist.destroy_process_group()
@@ -352,23 +523,44 @@ def run_ours(args):
                          "pipeline_frac": rows * BYTES_PER_ROW / (ms_dev * 1e-3) / 1e9 / peak},
             "phase_ms": per, "result_rows": result_rows, "clocks": clocks,
         }
+        line["parity"] = parity
+        line["phase_ms_meaning"] = {
+            "h2d": "host->device column copies, with the partition kernels that run chunk by chunk behind them (0 for device-resident input)",
+            "exchange": "several GPUs: gather of the peers' arrival counters (rows are pulled inside `group`); exact partition: exposed NCCL all-to-all",
+            "sync": "several GPUs: waiting for the other ranks at the job's two barriers (arrival skew + barrier latency)"}
         if world == 1 and not args.no_cpu:
             from oracle import c_oracle
-            cores = os.cpu_count() or 1
-            t = synth.make_flows(args.ref_series, n, seed=1)
+            cores = cpu_threads()
+            ref_series = args.ref_series or S
+            t = synth.torch_cols_to_numpy(cols_t) if ref_series == S else synth.make_flows(ref_series, n, seed=1)
             c_oracle.build()
             c_oracle.run_job(t, algo=0, threads=cores)
             t0 = time.perf_counter()
-            reps = 3
+            reps = 2
             for _ in range(reps):
                 c_oracle.run_job(t, algo=0, threads=cores)
             dt = (time.perf_counter() - t0) / reps
-            line["cpu_baseline"] = {"value": len(t["value"]) / dt, "unit": "records/s", "cores": cores, "kind": "port",
-                                    "sample": "%d rows x %d reps, oracle/tad_oracle.c OpenMP" % (len(t["value"]), reps),
+            line["cpu_baseline"] = {"value": len(t["value"]) / dt, "unit": "records/s", "cores": cores, "threads_used": cores,
+                                    "kind": "port",
+                                    "omp": {k: os.environ.get(k) for k in ("OMP_PROC_BIND", "OMP_PLACES", "OMP_NUM_THREADS")},
+                                    "sample": "the bench table itself, %d rows x %d reps (+1 warm-up), oracle/tad_oracle.c OpenMP" % (len(t["value"]), reps),
                                     "python_port_1core": python_port_rate(n)}
+            del t
             line["native_ingest"] = native_decode_rate()
-        print(json.dumps(line))
     hcols.free()
+    del dcols, cols_t
+    torch.cuda.empty_cache()
+    if rank == 0:
+        if world == 1 and not args.no_sides and args.algo == "EWMA":
+            # the other BASELINE configurations, measured in the same run on the same GPU (device-resident input)
+            line["side"] = [
+                side_run(eng, dev, "DBSCAN", 10_000_000, 24, steps=3, warmup=1,
+                         name="BASELINE configs[3]: DBSCAN over 10M connections x 24 points (240M records)"),
+                side_run(eng, dev, "ARIMA", 20_000, 100, steps=1, warmup=1,
+                         name="BASELINE configs[2] slice: ARIMA per-series fit + score, 20K connections x 100 points "
+                              "(2M records; the named 1B-record size is reported as fits/s x its 1e7 connections)"),
+            ]
+        print(json.dumps(line))
     eng.close()
     if dist is not None:
         dist.destroy_process_group()
@@ -382,7 +574,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--series", type=int, default=1_000_000)
     ap.add_argument("--points", type=int, default=100)
-    ap.add_argument("--ref-series", type=int, default=100_000, help="connections in the CPU sample")
+    ap.add_argument("--ref-series", type=int, default=0, help="connections in the CPU arm's table (0 = the full bench table)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the sampled oracle cross-check")
+    ap.add_argument("--no-sides", action="store_true", help="skip the DBSCAN / ARIMA side measurements (N = 1 only)")
     ap.add_argument("--algo", default="EWMA", choices=["EWMA", "DBSCAN", "ARIMA"],
                     help="detector (the BASELINE metric is EWMA; the others are side measurements of configs[2]/[3])")
     ap.add_argument("--no-cpu", action="store_true")

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define TAD_ABI_VERSION 1
+#define TAD_ABI_VERSION 2   /* 2: tad_job_spec.global_rows, TAD_PHASE_SYNC */
 
 typedef enum {
     TAD_OK = 0,
@@ -110,6 +110,10 @@ typedef struct {
     uint32_t n_ns_ignore;      /* --ns-ignore-list mapped to namespace ids                          */
     const uint32_t *ns_ignore;
     char id[40];               /* --id (uuid, 36 chars + NUL)                                       */
+    uint64_t global_rows;      /* world_size > 1: rows of the whole table over all ranks (the host  */
+                               /* knows it from its SELECT count()); every rank must pass the same   */
+                               /* value.  0 = the ranks agree on it with a blocking all-gather at    */
+                               /* job start.  Ignored on a single GPU.                               */
 } tad_job_spec;
 
 enum {
@@ -117,11 +121,14 @@ enum {
     TAD_PHASE_HIST,            /* key pack + hash + bucket histogram                                */
     TAD_PHASE_SCAN,            /* bucket offsets                                                    */
     TAD_PHASE_SCATTER,         /* hash partition into 32-byte packed rows                           */
-    TAD_PHASE_EXCHANGE,        /* multi-GPU all-to-all (0 on one GPU)                               */
+    TAD_PHASE_EXCHANGE,        /* multi-GPU: exposed part of the NCCL all-to-all (exact partition), or the  */
+                               /* peer counter gather (optimistic partition: rows are pulled inside GROUP)  */
     TAD_PHASE_GROUP,           /* per-bucket group + time sort + reduce -> per-series arrays        */
     TAD_PHASE_SPILL,           /* oversized buckets through the global-memory path                  */
     TAD_PHASE_DETECT,          /* stddev_samp + EWMA/ARIMA/DBSCAN + anomaly compaction              */
     TAD_PHASE_D2H,             /* result rows device -> host                                        */
+    TAD_PHASE_SYNC,            /* multi-GPU: time spent waiting for the other ranks at the job's     */
+                               /* barriers (arrival skew + barrier latency; 0 on one GPU)            */
     TAD_NPHASES
 };
 

@@ -24,7 +24,7 @@ def test_header_symbols_exported():
 
 def test_abi_version_and_strerror():
     L = _lib.load()
-    assert L.tad_abi_version() == 1
+    assert L.tad_abi_version() == 2
     assert L.tad_strerror(0) == b"ok"
     assert L.tad_strerror(-1) == b"invalid argument"
     assert L.tad_strerror(-99) == b"unknown error"
@@ -34,9 +34,9 @@ def test_struct_sizes_match_header():
     # sizes the cgo/ctypes bindings rely on (LP64)
     assert ctypes.sizeof(_lib.TadConfig) == 32
     assert ctypes.sizeof(_lib.TadColumns) == 24 + 10 * 8
-    assert ctypes.sizeof(_lib.TadJobSpec) == 24 + 8 + 40
+    assert ctypes.sizeof(_lib.TadJobSpec) == 24 + 8 + 40 + 8
     assert ctypes.sizeof(_lib.TadRows) == 8 + 11 * 8
-    assert ctypes.sizeof(_lib.TadStatus) == 16 + 256 + 8 * 8 + 2 * 8 + 9 * 8
+    assert ctypes.sizeof(_lib.TadStatus) == 16 + 256 + 8 * 8 + 2 * 8 + 10 * 8
 
 
 def test_header_is_valid_c99_and_cxx_and_example_links(tmp_path):

@@ -31,22 +31,26 @@ def test_owner_rank_mirror():
     assert sum(len(p["value"]) for p in parts) == len(t["value"])
 
 
-def test_two_ranks_gloo_cpu(tmp_path):
-    _launch("cpu", 2, tmp_path, 29611)
+@pytest.mark.parametrize("world", [2, 4])
+def test_ranks_gloo_cpu(tmp_path, world):
+    _launch("cpu", world, tmp_path, 29611 + world)
 
 
 @pytest.mark.gpu
-def test_two_ranks_nccl_exchange(tmp_path):
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_ranks_on_gpus_match_the_oracle(tmp_path, world):
+    """Union of the ranks' result rows == the oracle's rows on the whole table (anomaly_detection.py:680-684: the grouping must
+    survive the sharding), for the peer-pull path, its fallback and the NCCL exchange; every result column bit-exact."""
     import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    from tests.multi_worker import case_table
     from tests.util import assert_same_rows, oracle_rows
-    _launch("gpu", 2, tmp_path, 29612)
-    table = synth.make_flows(4000, 40, seed=77, dup_frac=0.05, ragged=True)
-    t2 = synth.make_flows(2, 6000, seed=78)
-    table = {k: np.concatenate([table[k], t2[k]]) for k in table}
-    for algo in ("EWMA", "DBSCAN"):
-        parts = [np.load(os.path.join(tmp_path, "res_%s_%d.npz" % (algo, r))) for r in range(2)]
-        got = {k: np.concatenate([p[k] for p in parts]) for k in parts[0].files}
-        want, _, _ = oracle_rows(table, algo, emit_all=True)
-        assert_same_rows(got, want, what="2-rank " + algo)
+    _launch("gpu", world, tmp_path, 29620 + world)
+    for name, algos in (("spread", ("EWMA", "DBSCAN")), ("skewed", ("EWMA", "DBSCAN")), ("nccl", ("EWMA",))):
+        table = case_table("spread" if name == "nccl" else name)
+        for algo in algos:
+            parts = [np.load(os.path.join(tmp_path, "res_%s_%s_%d.npz" % (name, algo, r))) for r in range(world)]
+            got = {k: np.concatenate([p[k] for p in parts]) for k in parts[0].files}
+            want, _, _ = oracle_rows(table, algo, emit_all=True)
+            assert_same_rows(got, want, what="%d ranks, %s, %s" % (world, name, algo))

@@ -9,8 +9,8 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libtheia_tad.so")
 
-TAD_NPHASES = 9
-PHASE_NAMES = ("h2d", "hist", "scan", "scatter", "exchange", "group", "spill", "detect", "d2h")
+TAD_NPHASES = 10
+PHASE_NAMES = ("h2d", "hist", "scan", "scatter", "exchange", "group", "spill", "detect", "d2h", "sync")
 ALGOS = {"EWMA": 0, "ARIMA": 1, "DBSCAN": 2}
 STATE_NAMES = ("NEW", "SCHEDULED", "RUNNING", "COMPLETED", "FAILED")
 TAD_MEM_HOST, TAD_MEM_DEVICE = 0, 1
@@ -37,7 +37,8 @@ class TadColumns(C.Structure):
 
 class TadJobSpec(C.Structure):
     _fields_ = [("algo", C.c_int32), ("reducer", C.c_int32), ("start_time", C.c_uint32), ("end_time", C.c_uint32),
-                ("flags", C.c_uint32), ("n_ns_ignore", C.c_uint32), ("ns_ignore", C.c_void_p), ("id", C.c_char * 40)]
+                ("flags", C.c_uint32), ("n_ns_ignore", C.c_uint32), ("ns_ignore", C.c_void_p), ("id", C.c_char * 40),
+                ("global_rows", C.c_uint64)]
 
 
 class TadStatus(C.Structure):

@@ -52,10 +52,28 @@ struct RowFilter {
 constexpr int kMaxSeg = 32;          // 8 source ranks x 4 exchange chunks
 struct SegDesc {
     const Row32 *base[kMaxSeg];
-    const uint32_t *off[kMaxSeg];
+    const uint32_t *off[kMaxSeg];   // stride == 0: exclusive row offsets (B_local + 1); stride != 0 && nseg > 1: row COUNTS (B_local)
     int nseg;
-    uint32_t stride;      // != 0 (single segment only): bucket b starts at base[0] + b * stride (fixed-capacity slots)
+    uint32_t stride;      // != 0: fixed-capacity slots (optimistic partition): local bucket b of segment s starts at
+                          // base[s] + (b_lo + b) * stride.  One segment on a single GPU (the slot holds min(count, stride)
+                          // rows, the rest sits in the overflow list); one segment PER SOURCE RANK on several GPUs, where
+                          // base[s] is rank s's partition buffer mapped into this process (CUDA IPC) and the rows are
+                          // pulled over NVLink -- no exchange step, no receive buffer.
+    uint32_t b_lo;        // first global bucket of this rank's range (0 on a single GPU)
 };
+
+// rows of local bucket `bkt` that segment `sg` holds, and where they start (n_total: the bucket's total, single segment only)
+__host__ __device__ __forceinline__ void seg_span(const SegDesc &seg, int sg, uint32_t bkt, uint32_t n_total, uint32_t &first,
+                                                  uint32_t &count)
+{
+    if (seg.stride) {
+        first = (seg.b_lo + bkt) * seg.stride;
+        count = seg.nseg == 1 ? n_total : seg.off[sg][bkt];
+    } else {
+        first = seg.off[sg][bkt];
+        count = seg.off[sg][bkt + 1] - first;
+    }
+}
 
 struct OutCols {
     uint32_t *src_ip, *dst_ip, *flow_start, *flow_end;
@@ -90,6 +108,8 @@ enum {
     ST_NCLS1,
     ST_NCLS2,
     ST_OVF,             // optimistic partition: rows that did not fit their bucket's fixed-capacity slot
+    ST_LOCALKEPT,       // multi-GPU optimistic partition: rows of THIS rank that passed the filters (ST_KEPT = rows owned);
+                        // must follow ST_OVF: the two travel in one 8-byte all-gather
     ST_COUNT
 };
 

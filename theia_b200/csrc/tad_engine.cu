@@ -88,6 +88,14 @@ struct tad_ctx {
     std::mutex pool_mu;
     std::vector<PinnedBlock> pinned_pool;
     NcclComm nccl;
+    // multi-GPU optimistic partition + peer pull: every rank scatters into fixed-capacity slots of an
+    // exported buffer (arrival counters in front, slots behind), the peers map it (CUDA IPC) and the owner's group kernel
+    // pulls its bucket segments over NVLink -- no histogram pass, no all-to-all, no receive buffer.
+    int peer_pull = 1;                              // TAD_PEER_PULL=0: always the exact partition + NCCL all-to-all
+    DevBuf xbuf;                                    // exported: [counters: B x u32, padded][slots: B x slot x Row32]
+    void *peer_x[kMaxRanks]{};                      // peers' xbuf mapped into this process
+    bool peers_mapped = false;
+    DevBuf xcnt, xtotal;                            // per-source counts / totals of the owned bucket range
 };
 
 namespace {
@@ -337,7 +345,9 @@ void run_job(tad_ctx *ctx, tad_job *job)
     uint64_t R_total = R;
     ensure(ctx->small, 4096);
     unsigned long long *d_small = static_cast<unsigned long long *>(ctx->small.p);
-    if (world > 1) {
+    if (world > 1 && sp.global_rows) {
+        R_total = sp.global_rows;      // the host counted the table: no start-of-job collective, no host sync
+    } else if (world > 1) {
         // global row count -> same bucket count on every rank
         ctx->h_small[0] = R;
         CU(cudaMemcpyAsync(d_small, ctx->h_small, 8, cudaMemcpyHostToDevice, st));
@@ -440,6 +450,113 @@ void run_job(tad_ctx *ctx, tad_job *job)
             CU(cudaMemsetAsync(d_stats, 0, 64 * sizeof(uint32_t), st));      // discard; redo exactly
         }
     }
+
+    // ---- several GPUs, optimistic partition + peer pull ---------------------------------------------------------------
+    // Every rank scatters its rows into fixed-capacity slots of ALL global buckets (slot = kGroupCap / world rows: a
+    // source holds 1/world of a bucket on average) inside a buffer its peers have mapped with CUDA IPC.  One 8-byte
+    // all-gather after the scatter is the barrier "every rank's slots are complete" and carries the overflow counts: if
+    // any slot overflowed anywhere, all ranks take the exact path below (same decision everywhere: it is made on the
+    // gathered data).  Otherwise each rank reads the arrival counters of its bucket range out of the peers' buffers and
+    // its group kernel pulls the rows themselves, segment by segment, with the bulk copies it issues anyway.
+    const uint32_t slotM = std::max<uint32_t>(256u, (uint32_t)kGroupCap / (uint32_t)world);
+    const size_t x_cnt_bytes = (((size_t)B * 4) + 65535) & ~size_t(65535);
+    const size_t x_need = x_cnt_bytes + (size_t)B * slotM * sizeof(Row32);
+    bool sync_at_end = false;
+    if (world > 1 && ctx->peer_pull && ctx->optimistic && R_total > 0 && (uint64_t)B * slotM <= (1ull << 31) &&
+        x_need <= (48ull << 30)) {
+        auto gather16 = [&]() {        // blocking 128-byte all-gather through pinned memory (regrow only)
+            CU(cudaMemcpyAsync(d_small, ctx->h_small, 16 * 8, cudaMemcpyHostToDevice, st));
+            if (nccl_allgather(&ctx->nccl, d_small, d_small + 16, 16 * 8, st)) fail(TAD_ERR_NCCL, "%s", nccl_last_error());
+            CU(cudaMemcpyAsync(ctx->h_small + 16, d_small + 16, 16 * 8 * world, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+        };
+        if (x_need > ctx->xbuf.cap || !ctx->peers_mapped) {
+            // Regrow (first job, or a larger table).  x_need depends only on the global bucket count, so every rank
+            // takes this branch in the same job: unmap, barrier (nobody maps a buffer that is about to be freed),
+            // reallocate, exchange the IPC handles, map.
+            static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+            for (int r = 0; r < world; r++)
+                if (ctx->peer_x[r]) { CU(cudaIpcCloseMemHandle(ctx->peer_x[r])); ctx->peer_x[r] = nullptr; }
+            ctx->peers_mapped = false;
+            memset(ctx->h_small, 0, 16 * 8);
+            gather16();
+            ensure(ctx->xbuf, x_need);
+            cudaIpcMemHandle_t mine;
+            CU(cudaIpcGetMemHandle(&mine, ctx->xbuf.p));
+            memset(ctx->h_small, 0, 16 * 8);
+            ctx->h_small[0] = ctx->xbuf.cap;
+            memcpy(ctx->h_small + 2, &mine, sizeof(mine));
+            gather16();
+            for (int r = 0; r < world; r++) {
+                if (r == me) continue;
+                cudaIpcMemHandle_t h;
+                memcpy(&h, ctx->h_small + 16 + 16 * r + 2, sizeof(h));
+                if (ctx->h_small[16 + 16 * r] < x_need) fail(TAD_ERR_INTERNAL, "rank %d exports a smaller partition buffer", r);
+                cudaError_t e = cudaIpcOpenMemHandle(&ctx->peer_x[r], h, cudaIpcMemLazyEnablePeerAccess);
+                if (e != cudaSuccess) {
+                    cudaGetLastError();
+                    ctx->peer_x[r] = nullptr;
+                    fail(TAD_ERR_CUDA, "cannot map the partition buffer of rank %d (%s); set TAD_PEER_PULL=0 on every rank to "
+                                       "exchange rows through NCCL instead", r, cudaGetErrorString(e));
+                }
+            }
+            ctx->peers_mapped = true;
+        }
+        uint32_t *xcursor = static_cast<uint32_t *>(ctx->xbuf.p);
+        Row32 *xpart = reinterpret_cast<Row32 *>(static_cast<char *>(ctx->xbuf.p) + x_cnt_bytes);
+        ensure(ctx->xcnt, (size_t)Bl * 4 * world);
+        ensure(ctx->xtotal, (size_t)Bl * 4);
+        uint32_t *xcnt = (uint32_t *)ctx->xcnt.p, *xtotal = (uint32_t *)ctx->xtotal.p;
+        CU(cudaMemsetAsync(xcursor, 0, (size_t)B * 4, st));
+        mark(-1);
+        if (host_input) {
+            for (int k = 0; k < nchunks; k++) {
+                uint64_t lo, hi;
+                chunk_range(k, lo, hi);
+                CU(cudaStreamWaitEvent(st, ctx->chunk_ev[k], 0));
+                if (hi <= lo) continue;
+                CU(launch_scatter(st, offset_cols(lo), hi - lo, f, logB, xcursor, xpart, slotM, nullptr, 0, d_stats + ST_OVF)); launches++;
+            }
+            mark(TAD_PHASE_H2D);          // copy + overlapped scatter of all chunks
+        } else {
+            CU(launch_scatter(st, c, R, f, logB, xcursor, xpart, slotM, nullptr, 0, d_stats + ST_OVF)); launches += R ? 1 : 0;
+            mark(TAD_PHASE_SCATTER);
+        }
+        // barrier + overflow agreement: {overflow rows, -} of every rank
+        if (nccl_allgather(&ctx->nccl, d_stats + ST_OVF, d_small + 32, 8, st)) fail(TAD_ERR_NCCL, "%s", nccl_last_error());
+        mark(TAD_PHASE_SYNC);
+        PeerCounters pc{};
+        for (int r = 0; r < world; r++) pc.p[r] = r == me ? xcursor : static_cast<const uint32_t *>(ctx->peer_x[r]);
+        CU(launch_gather_counts(st, pc, world, b_lo, Bl, slotM, xcnt, xtotal, xcursor, B, d_stats + ST_LOCALKEPT)); launches += 2;
+        mark(TAD_PHASE_EXCHANGE);
+        CU(launch_bucket_scan(st, xtotal, offsets, cursor, Bl, kGroupCap, big_list, big_base, cls_list, d_stats,
+                              ctx->scan_sync.p, ++ctx->scan_epoch)); launches++;
+        mark(TAD_PHASE_SCAN);
+        CU(cudaMemcpyAsync(ctx->h_stats, d_stats, ST_COUNT * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(ctx->h_small + 32, d_small + 32, 8 * world, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        check_cancel();
+        uint64_t any_ovf = 0;
+        for (int r = 0; r < world; r++) any_ovf += (uint32_t)ctx->h_small[32 + r];
+        sync_at_end = true;       // peers may still read this rank's slots: no rank starts its next job before all are done
+        if (any_ovf == 0) {
+            partitioned = true;
+            kept = ctx->h_stats[ST_LOCALKEPT];
+            owned = ctx->h_stats[ST_KEPT];
+            seg.nseg = world;
+            seg.stride = slotM;
+            seg.b_lo = b_lo;
+            for (int r = 0; r < world; r++) {
+                const char *xb = r == me ? static_cast<const char *>(ctx->xbuf.p) : static_cast<const char *>(ctx->peer_x[r]);
+                seg.base[r] = reinterpret_cast<const Row32 *>(xb + x_cnt_bytes);
+                seg.off[r] = xcnt + (size_t)r * Bl;
+            }
+            ensure(ctx->entries, (owned ? owned : 1) * sizeof(SeriesEntry));
+            entries = static_cast<SeriesEntry *>(ctx->entries.p);
+        } else {
+            CU(cudaMemsetAsync(d_stats, 0, 64 * sizeof(uint32_t), st));      // discard; redo exactly (every rank does)
+        }
+    }
     if (world == 1 && !partitioned) {
         CU(cudaMemsetAsync(hist, 0, (size_t)B * 4, st));
         mark(-1);
@@ -469,8 +586,8 @@ void run_job(tad_ctx *ctx, tad_job *job)
         seg.base[0] = part;
         seg.off[0] = offsets;
         entries = reinterpret_cast<SeriesEntry *>(part);      // in place over the staged bucket rows
-    } else if (world > 1) {
-        // ---- multi GPU: K row chunks; chunk c is sent over NVLink (comm stream) while chunk c+1 is scattered ------
+    } else if (world > 1 && !partitioned) {
+        // ---- multi GPU, exact partition: K row chunks; chunk c is sent over NVLink (comm stream) while chunk c+1 is scattered ------
         // chunked (overlapped) exchange pays off at N = 2 (measured 11.5 -> 9.6 ms); at N >= 4 the NVLink all-to-all is
         // longer than the scatter it could hide behind and the extra segments cost the group kernel more than is won
         const int K = (R >= ctx->exchange_min_rows && (world == 2 || ctx->exchange_chunks_forced)) ? ctx->exchange_chunks : 1;
@@ -646,6 +763,13 @@ void run_job(tad_ctx *ctx, tad_job *job)
     }
     check_cancel();
     set_progress(job, TAD_STATE_RUNNING, 5);
+    if (sync_at_end) {
+        // end-of-job barrier of the peer-pull path: my slots and counters may be overwritten (next job) only after every
+        // peer's group kernel has read them; its wait is the ranks' arrival skew, accounted as TAD_PHASE_SYNC
+        mark(-1);
+        if (nccl_allgather(&ctx->nccl, d_small + 48, d_small + 56, 8, st)) fail(TAD_ERR_NCCL, "%s", nccl_last_error());
+        mark(TAD_PHASE_SYNC);
+    }
 
     // ---- egress: result rows -> pinned host memory -------------------------------------------
     mark(-1);
@@ -682,7 +806,7 @@ void run_job(tad_ctx *ctx, tad_job *job)
     for (int i = 0; i < nev; i++) {
         if ((ev_phase[i] == TAD_PHASE_HIST || ev_phase[i] == TAD_PHASE_H2D || ev_phase[i] == TAD_PHASE_SCATTER) && first_k < 0)
             first_k = i - 1;
-        if (ev_phase[i] == TAD_PHASE_DETECT) last_k = i;
+        if (ev_phase[i] == TAD_PHASE_DETECT || (ev_phase[i] == TAD_PHASE_SYNC && last_k >= 0)) last_k = i;
     }
     if (first_k >= 0 && last_k > first_k) CU(cudaEventElapsedTime(&total, ctx->ev[first_k], ctx->ev[last_k]));
     {
@@ -823,6 +947,7 @@ int tad_init(const tad_config *cfg, tad_ctx **out)
     ok = ok && cudaEventCreateWithFlags(&ctx->start_ev, cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; ok && i <= kMaxXChunks; i++) ok = cudaEventCreateWithFlags(&ctx->x_ev[i], cudaEventDisableTiming) == cudaSuccess;
     if (const char *e = getenv("TAD_OPTIMISTIC")) ctx->optimistic = atoi(e);
+    if (const char *e = getenv("TAD_PEER_PULL")) ctx->peer_pull = atoi(e);
     if (const char *e = getenv("TAD_EXCHANGE_MIN_ROWS")) ctx->exchange_min_rows = strtoull(e, nullptr, 10);
     if (getenv("TAD_EXCHANGE_CHUNKS")) ctx->exchange_chunks_forced = true;
     if (const char *e = getenv("TAD_EXCHANGE_CHUNKS")) ctx->exchange_chunks = atoi(e) < 1 ? 1 : (atoi(e) > kMaxXChunks ? kMaxXChunks : atoi(e));
@@ -855,8 +980,16 @@ void tad_shutdown(tad_ctx *ctx)
     ctx->cv.notify_all();
     if (ctx->worker.joinable()) ctx->worker.join();
     cudaSetDevice(ctx->cfg.device);
+    if (ctx->peers_mapped && ctx->nccl.comm && ctx->small.p && ctx->stream) {
+        // an exported buffer must outlive every peer's mapping of it: unmap, meet the peers, only then free
+        for (int r = 0; r < kMaxRanks; r++)
+            if (ctx->peer_x[r]) { cudaIpcCloseMemHandle(ctx->peer_x[r]); ctx->peer_x[r] = nullptr; }
+        unsigned long long *d = static_cast<unsigned long long *>(ctx->small.p);
+        if (nccl_allgather(&ctx->nccl, d + 48, d + 56, 8, ctx->stream) == 0) cudaStreamSynchronize(ctx->stream);
+        ctx->peers_mapped = false;
+    }
     nccl_comm_destroy(&ctx->nccl);
-    DevBuf *bufs[] = {&ctx->hist, &ctx->offsets, &ctx->cursor, &ctx->big_list, &ctx->big_base, &ctx->cls_list, &ctx->csr_p, &ctx->stats, &ctx->part, &ctx->csr_v,
+    DevBuf *bufs[] = {&ctx->xbuf, &ctx->xcnt, &ctx->xtotal, &ctx->hist, &ctx->offsets, &ctx->cursor, &ctx->big_list, &ctx->big_base, &ctx->cls_list, &ctx->csr_p, &ctx->stats, &ctx->part, &ctx->csr_v,
                       &ctx->csr_t, &ctx->nsb, &ctx->npb, &ctx->sbase, &ctx->outb, &ctx->ns_ignore, &ctx->spill, &ctx->dbx,
                       &ctx->dbi, &ctx->exch, &ctx->scan_sync, &ctx->small, &ctx->hist_all, &ctx->seg_off, &ctx->seg_total,
                       &ctx->entries, &ctx->ar_y, &ctx->ar_pred, &ctx->ar_lam, &ctx->ovf};

@@ -523,10 +523,7 @@ __global__ void __launch_bounds__(NT) group_kernel(const SegDesc seg, SeriesEntr
         if (tid == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
         __syncwarp();
         uint32_t so = 0, sc = 0;
-        if (tid < seg.nseg) {
-            so = seg.stride ? bkt * seg.stride : seg.off[tid][bkt];
-            sc = seg.stride ? n : seg.off[tid][bkt + 1] - so;
-        }
+        if (tid < seg.nseg) seg_span(seg, tid, bkt, n, so, sc);
         uint32_t inc = sc;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -1395,6 +1392,56 @@ __global__ void __launch_bounds__(256) segment_total_kernel(const uint32_t *__re
         for (int r = 0; r < nseg; r++) t += hist_all[(size_t)r * B_global + b_lo + i];
         total[i] = t;
     }
+}
+
+// ----------------------------------------------------------------------------------------
+// multi-GPU, optimistic partition + peer pull: the arrival counters of this rank's bucket range, read out of every
+// source rank's (IPC-mapped) counter array over NVLink.  cnt[s * B_local + b] = rows source s holds for local bucket b
+// (they sit in slot b_lo + b of s's partition buffer), total[b] = the bucket's size.
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t ld_sys_u32(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(256) gather_counts_kernel(const PeerCounters pc, int world, uint32_t b_lo, uint32_t B_local,
+                                                            uint32_t slot, uint32_t *__restrict__ cnt, uint32_t *__restrict__ total)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < B_local; i += gridDim.x * blockDim.x) {
+        uint32_t c[8], t = 0;
+#pragma unroll
+        for (int r = 0; r < 8; r++) c[r] = r < world ? ld_sys_u32(pc.p[r] + b_lo + i) : 0u;      // all loads in flight
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            if (r < world) {
+                const uint32_t k = min(c[r], slot);
+                cnt[(size_t)r * B_local + i] = k;
+                t += k;
+            }
+        }
+        total[i] = t;
+    }
+}
+
+__global__ void __launch_bounds__(256) sum_counters_kernel(const uint32_t *__restrict__ a, uint32_t n, uint32_t *__restrict__ out)
+{
+    unsigned long long acc = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) acc += a[i];
+    for (int d = 16; d; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, (uint32_t)acc);
+}
+
+cudaError_t launch_gather_counts(cudaStream_t st, const PeerCounters &pc, int world, uint32_t b_lo, uint32_t B_local, uint32_t slot,
+                                 uint32_t *cnt, uint32_t *total, const uint32_t *my_counters, uint32_t B_global, uint32_t *kept_out)
+{
+    if (world > 8) return cudaErrorInvalidValue;
+    const uint32_t g1 = (B_local + 255) / 256, g2 = (B_global + 255) / 256;
+    const uint32_t cap = (uint32_t)num_sms() * 8;
+    gather_counts_kernel<<<g1 > cap ? cap : g1, 256, 0, st>>>(pc, world, b_lo, B_local, slot, cnt, total);
+    sum_counters_kernel<<<g2 > cap ? cap : g2, 256, 0, st>>>(my_counters, B_global, kept_out);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_segment_scan(cudaStream_t st, const uint32_t *hist_all, uint32_t B_global, uint32_t b_lo, uint32_t B_local,

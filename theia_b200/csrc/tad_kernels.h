@@ -54,6 +54,12 @@ cudaError_t run_spill(cudaStream_t st, const SegDesc &seg, SeriesEntry *entries,
 }  // namespace tad
 
 namespace tad {
+// Multi-GPU, optimistic partition: pc.p[s] = source rank s's arrival counters (its own for s = me, IPC-mapped otherwise).
+// Fills cnt[world x B_local] / total[B_local] for the owned bucket range and adds the sum of this rank's own B_global
+// counters (= its rows that passed the filters) to *kept_out.  Two launches.
+struct PeerCounters { const uint32_t *p[8]; };
+cudaError_t launch_gather_counts(cudaStream_t st, const PeerCounters &pc, int world, uint32_t b_lo, uint32_t B_local, uint32_t slot,
+                                 uint32_t *cnt, uint32_t *total, const uint32_t *my_counters, uint32_t B_global, uint32_t *kept_out);
 // Multi-GPU: per-source segment offsets and total bucket sizes of this rank's bucket range from the
 // all-gathered histograms.  hist_all[r * B_global + b]; range = [b_lo, b_lo + B_local).
 cudaError_t launch_segment_scan(cudaStream_t st, const uint32_t *hist_all, uint32_t B_global, uint32_t b_lo, uint32_t B_local,

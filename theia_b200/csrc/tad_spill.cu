@@ -42,8 +42,8 @@ __global__ void __launch_bounds__(256) spill_gather_kernel(const SegDesc seg, co
     const uint32_t j = blockIdx.x;
     const uint32_t b = big_list[j];
     uint32_t base = big_base[j];
-    if (seg.stride) {
-        // optimistic partition: the slot holds the first `stride` rows; they are packed at j * stride (the
+    if (seg.stride && seg.nseg == 1) {
+        // optimistic partition, one GPU: the slot holds the first `stride` rows; they are packed at j * stride (the
         // overflow rows follow after all slots; the sort that comes next does not care about input order)
         const Row32 *rows = seg.base[0] + (size_t)b * seg.stride;
         for (uint32_t i = threadIdx.x; i < seg.stride; i += blockDim.x) {
@@ -51,8 +51,11 @@ __global__ void __launch_bounds__(256) spill_gather_kernel(const SegDesc seg, co
         }
         return;
     }
+    // exact partition, or the multi-GPU optimistic one (every source's slot holds all of its rows: an overflow anywhere
+    // sends the whole job down the exact path): the bucket is the concatenation of its per-source pieces
     for (int sg = 0; sg < seg.nseg; sg++) {
-        const uint32_t off = seg.off[sg][b], n = seg.off[sg][b + 1] - off;
+        uint32_t off, n;
+        seg_span(seg, sg, b, 0u, off, n);
         const Row32 *rows = seg.base[sg] + off;
         for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
             in[base + i] = to_spill(rows[i]);
@@ -182,7 +185,7 @@ cudaError_t run_spill(cudaStream_t st, const SegDesc &seg, SeriesEntry *entries,
     size_t temp_bytes = cub_temp_bytes(M);
 
     spill_gather_kernel<<<n_big, 256, 0, st>>>(seg, big_list, big_base, in);
-    if (seg.stride) {
+    if (seg.stride && seg.nseg == 1) {
         if ((uint64_t)n_big * seg.stride + n_ovf != big_rows) return cudaErrorInvalidValue;
         if (n_ovf) spill_append_kernel<<<(n_ovf + 255) / 256, 256, 0, st>>>(ovf, n_ovf, in + (size_t)n_big * seg.stride);
     }

@@ -176,13 +176,14 @@ class TadEngine:
         return self.alloc_columns(max(1, len(table["flow_end"]))).fill(table)
 
     def submit(self, cols, algo="EWMA", reducer: int = L.TAD_REDUCE_MAX, start_time: int = 0, end_time: int = 0,
-               tad_id: str = "", emit_all: bool = False, ns_ignore=(), check: bool = True) -> Job:
+               tad_id: str = "", emit_all: bool = False, ns_ignore=(), check: bool = True, global_rows: int = 0) -> Job:
         spec = L.TadJobSpec()
         spec.algo = L.ALGOS[algo] if isinstance(algo, str) else int(algo)
         spec.reducer = reducer
         spec.start_time, spec.end_time = int(start_time), int(end_time)
         spec.flags = L.TAD_FLAG_EMIT_ALL if emit_all else 0
         spec.id = tad_id.encode()[:39]
+        spec.global_rows = int(global_rows)
         keep = [cols]
         if len(ns_ignore):
             arr = np.asarray(ns_ignore, dtype=np.uint32)

@@ -97,11 +97,13 @@ def golden_e2e_table(values, shuffle_seed: int | None = 7, duplicates: int = 0) 
     return cols
 
 
-def make_flows_torch(n_series: int, points_per_series: int, seed: int, device):
+def make_flows_torch(n_series: int, points_per_series: int, seed: int, device, noisy: bool = False):
     """Same distribution as ``make_flows`` (fixed length, no duplicates), generated on
     ``device`` with torch ops; returns a dict of torch tensors with the column dtypes
     widened to what torch supports (u16 -> int16 bit pattern, u32 -> int32, u64 -> int64;
-    the engine reads raw bytes, so only the bit patterns matter)."""
+    the engine reads raw bytes, so only the bit patterns matter).  ``noisy``: throughputs of a few hundred with 15 %
+    noise and 4 % spikes instead of 1e6..1e10 with 0.1 % noise -- the regime in which ARIMA's Box-Cox transform is
+    well conditioned (near-constant series make the reference's calculate_arima fail inside its blanket except)."""
     import torch
     g = torch.Generator(device=device)
     g.manual_seed(seed)
@@ -120,13 +122,15 @@ def make_flows_torch(n_series: int, points_per_series: int, seed: int, device):
     flow_start = T0 + ri(0, 3600, S)
     base = torch.exp(torch.empty(S, device=device, dtype=torch.float64).uniform_(
         float(np.log(1e6)), float(np.log(1e10)), generator=g))
+    if noisy:
+        base = torch.empty(S, device=device, dtype=torch.float64).uniform_(50.0, 500.0, generator=g)
     perm = torch.randperm(R, generator=g, device=device)         # global shuffle
     sid = perm // n
     k = perm % n + 1
     b = base[sid]
-    val = b + torch.randn(R, generator=g, device=device, dtype=torch.float64) * (1e-3 * b)
-    spike = torch.rand(R, generator=g, device=device) < 0.01
-    fac = torch.as_tensor(SPIKE_FACTORS, device=device)[ri(0, 3, R)]
+    val = b + torch.randn(R, generator=g, device=device, dtype=torch.float64) * ((0.15 if noisy else 1e-3) * b)
+    spike = torch.rand(R, generator=g, device=device) < (0.04 if noisy else 0.01)
+    fac = torch.as_tensor(np.array([0.5, 2.0, 3.0]) if noisy else SPIKE_FACTORS, device=device)[ri(0, 3, R)]
     val = torch.where(spike, val * fac, val)
     val = torch.clamp(torch.round(val), min=1.0).to(torch.int64)
     del b, spike, fac, perm
@@ -141,9 +145,10 @@ def make_flows_torch(n_series: int, points_per_series: int, seed: int, device):
 
 
 def make_flows_torch_sharded(series_per_gpu: int, points_per_series: int, seed: int, device, rank: int, world: int):
-    """Rank `rank`'s shard of a table with world * series_per_gpu connections: every connection's points
-    are dealt round-robin over the ranks (point k lives on rank k % world), so each rank holds
-    series_per_gpu * points rows and NO connection is local before the exchange."""
+    """Rank `rank`'s shard of a table with world * series_per_gpu connections: global row g = sid * points + (k - 1) lives
+    on rank g % world, so every rank holds exactly series_per_gpu * points rows (series_per_gpu * points is a multiple of
+    world for the bench shapes; otherwise the shards differ by at most one row), every connection's points are spread over
+    all ranks and NO connection is local before the exchange."""
     import torch
     g = torch.Generator(device=device)
     g.manual_seed(seed)                      # same key attributes on every rank
@@ -163,18 +168,19 @@ def make_flows_torch_sharded(series_per_gpu: int, points_per_series: int, seed: 
         float(np.log(1e6)), float(np.log(1e10)), generator=g))
     g2 = torch.Generator(device=device)
     g2.manual_seed(seed * 1000 + 17 + rank)   # per-rank noise and shuffle
-    npl = (n - rank + world - 1) // world     # points k = rank+1, rank+1+world, ... <= n
-    R = S * npl
+    total = S * n
+    R = (total - rank + world - 1) // world   # global rows g = rank, rank + world, ... < total
     perm = torch.randperm(R, generator=g2, device=device)
-    sid = perm // npl
-    k = (perm % npl) * world + rank + 1       # 1..n, the points this rank holds
+    gl = perm * world + rank
+    sid = gl // n
+    k = gl % n + 1                            # 1..n
     b = base[sid]
     val = b + torch.randn(R, generator=g2, device=device, dtype=torch.float64) * (1e-3 * b)
     spike = torch.rand(R, generator=g2, device=device) < 0.01
     fac = torch.as_tensor(SPIKE_FACTORS, device=device)[ri(g2, 0, 3, R)]
     val = torch.where(spike, val * fac, val)
     val = torch.clamp(torch.round(val), min=1.0).to(torch.int64)
-    del b, spike, fac, perm
+    del b, spike, fac, perm, gl
     return {
         "src_ip": src_ip[sid].to(torch.int32), "src_port": src_port[sid].to(torch.int16),
         "dst_ip": dst_ip[sid].to(torch.int32), "dst_port": dst_port[sid].to(torch.int16),
@@ -182,3 +188,12 @@ def make_flows_torch_sharded(series_per_gpu: int, points_per_series: int, seed: 
         "flow_end": (flow_start[sid] + 60 * k).to(torch.int32),
         "value": val,
     }
+
+
+def torch_cols_to_numpy(cols_t: dict, mask=None) -> dict:
+    """Device columns (bit patterns in torch's signed dtypes) -> the numpy table the oracle takes; ``mask`` selects rows."""
+    out = {}
+    for name, dt in COLUMN_DTYPES.items():
+        v = cols_t[name] if mask is None else cols_t[name][mask]
+        out[name] = np.ascontiguousarray(v.cpu().numpy()).view(dt)
+    return out
