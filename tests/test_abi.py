@@ -73,3 +73,20 @@ def test_c_example_runs_on_the_gpu(tmp_path):
     out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stderr
     assert "1 series, 64 points" in out.stdout and "throughput 50007861276" in out.stdout and "6/6 stages" in out.stdout
+
+
+@pytest.mark.gpu
+def test_four_worker_threads_share_one_context(tmp_path):
+    """The header's threading contract (theia_tad.h: "a tad_ctx may be used from several threads", the controller runs 4
+    workers, pkg/controller/util.go:43): four pthreads submit / poll / read / release / cancel distinct jobs on one context;
+    every result equals the one the same table gave alone.  (profiles/r02 holds a compute-sanitizer run of the same binary.)"""
+    import shutil
+    import subprocess
+    gcc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else shutil.which("gcc")
+    exe = str(tmp_path / "tad_workers")
+    subprocess.check_call([gcc, "-std=c99", "-pthread", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "tad_workers.c"),
+                           "-L", os.path.join(ROOT, "theia_b200"), "-ltheia_tad",
+                           "-Wl,-rpath," + os.path.join(ROOT, "theia_b200"), "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "4 workers x 6 rounds on one context: 0 failures" in out.stdout

@@ -226,15 +226,41 @@ def test_sentinel_row_when_nothing_is_anomalous(engine):
 
 @pytest.mark.gpu
 def test_controller_state_machine(engine):
-    """NEW -> SCHEDULED -> COMPLETED with stage progress, result retrieval by id, deletion (controller.go:354-424)."""
+    """NEW -> SCHEDULED -> (RUNNING with stage progress) -> COMPLETED, result retrieval by id, deletion
+    (controller.go:354-424).  Dispatch and observation are decoupled: sync() never blocks on the job."""
     c = ctl.AnomalyDetectorController(engine)
     name = "tad-5ca1ab1e-0000-4000-8000-00000000beef"
     c.create(name, ctl.TADSpec(jobType="EWMA", aggFlow="svc"))
     st = c.sync(name, flows=_flows(seed=7))
     assert st.state == "SCHEDULED" and st.sparkApplication == name[4:]
-    st = c.sync(name)
+    seen = []
+    st = c.wait(name, observe=lambda s: seen.append((s.state, s.completedStages, s.totalStages)))
     assert st.state == "COMPLETED" and st.completedStages == st.totalStages == 6
+    assert all(a in ("SCHEDULED", "RUNNING", "COMPLETED") for a, _, _ in seen)
+    prog = [k for a, k, _ in seen if a == "RUNNING"]
+    assert prog == sorted(prog) and all(0 <= k <= 6 for k in prog)            # progress never goes backwards
     rows = c.results[name[4:]]
     assert rows and all(r["id"] == name[4:] for r in rows)
     c.delete(name)
     assert name not in c.crs and name[4:] not in c.results
+
+
+@pytest.mark.gpu
+def test_controller_observes_intermediate_progress_on_the_gpu(engine):
+    """A job long enough to be caught in flight (ARIMA, the slowest detector): the controller reports RUNNING with
+    0 < completedStages < totalStages before COMPLETED (controller_test.go:303-306 asserts an intermediate count too)."""
+    from theia_b200 import synth
+    fl = synth.make_flows(3000, 60, seed=12)
+    flows = {"sourceIP": fl["src_ip"], "destinationIP": fl["dst_ip"], "sourceTransportPort": fl["src_port"],
+             "destinationTransportPort": fl["dst_port"], "protocolIdentifier": fl["proto"], "flowStartSeconds": fl["flow_start"],
+             "flowEndSeconds": fl["flow_end"], "throughput": (fl["value"] % 500 + 50).astype(np.uint64)}
+    c = ctl.AnomalyDetectorController(engine)
+    name = "tad-5ca1ab1e-0000-4000-8000-0000000000a1"
+    c.create(name, ctl.TADSpec(jobType="ARIMA"))
+    assert c.sync(name, flows=flows).state == "SCHEDULED"
+    seen = []
+    st = c.wait(name, observe=lambda s: seen.append((s.state, s.completedStages, s.totalStages)))
+    assert st.state == "COMPLETED" and st.completedStages == st.totalStages == 6
+    mid = [(k, n) for a, k, n in seen if a == "RUNNING" and 0 < k < n]
+    assert mid, seen[-5:]
+    c.delete(name)

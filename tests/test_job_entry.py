@@ -87,7 +87,7 @@ def test_clickhouse_http_speaks_to_the_port_of_the_jdbc_url():
     finally:
         srv.shutdown()
     (q1, u1, k1, b1), (q2, u2, k2, b2) = seen
-    assert q1 == {"query": ["SELECT 1 FORMAT Native"], "database": ["default"]} and (u1, k1, b1) == ("u", "p", b"")
+    assert q1 == {"query": ["SELECT 1 FORMAT Native"], "database": ["default"], "wait_end_of_query": ["1"]} and (u1, k1, b1) == ("u", "p", b"")
     assert q2["query"] == ["INSERT INTO default.tadetector FORMAT Native"] and b2 == b"\\x01\\x02"
 
 
@@ -216,3 +216,91 @@ def test_main_svc_with_a_window_does_not_refilter_on_the_gpu():
     want, _ = ad.anomaly_detection(OracleEngine(), "EWMA", fl, tad_id="w", agg_flow="svc")
     got = chn.read_native(tr2.inserts[0][1])
     assert len(got["id"]) == len(want) > 1
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.gpu
+def test_main_on_the_gpu_engine_matches_the_oracle_engine(engine):
+    """main() with the REAL engine behind it (fake ClickHouse transport): argv -> SELECT ... FORMAT Native -> decode -> plan /
+    masks / dictionaries -> C ABI -> CUDA kernels -> tadetector INSERT block, byte-compared column by column with the block
+    the same argv produces on the oracle-backed engine double."""
+    from . import test_host_mirror as thm
+    from .test_host_mirror_on_oracle import OracleEngine
+    fl = thm._flows(seed=4)
+    types = dict(chn_types(fl))
+    stream = chn.write_native([(k, types[k], np.asarray(v).astype(np.uint32) if types[k] == "String" and np.asarray(v).dtype.kind in "iu" else v)
+                               for k, v in fl.items()])
+    for argv in (["--algo", "EWMA", "--id", "g1", "--ns-ignore-list", '["kube-system"]'],
+                 ["--algo", "EWMA", "--id", "g2", "--agg-flow", "svc", "--end_time", "2022-08-11 07:00:00"],
+                 ["--algo", "DBSCAN", "--id", "g3", "--agg-flow", "pod", "--pod-label", "web"],
+                 ["--algo", "EWMA", "--id", "g4", "--agg-flow", "external"]):
+        blocks = []
+        for eng in (engine, OracleEngine()):
+            tr = _FakeTransport(stream)
+            assert ad.main(argv, engine=eng, transport=tr) == 0
+            (name, body), = tr.inserts
+            assert name == "default.tadetector"
+            blocks.append(chn.read_native(body))
+        got, want = blocks
+        assert set(got) == set(want) and len(got["id"]) == len(want["id"]) > 1, argv
+        cols = [c for c in got if c != "timeCreated"] if "timeCreated" in got else list(got)
+        order = lambda b: np.lexsort(tuple(np.asarray(b[c]).astype(str) for c in sorted(cols)))
+        og, ow = order(got), order(want)
+        for c in cols:
+            assert np.array_equal(np.asarray(got[c])[og], np.asarray(want[c])[ow]), (argv, c)
+
+
+def test_clickhouse_errors_surface_and_only_ipv4_failures_fall_back(monkeypatch):
+    """a 200 response that carries X-ClickHouse-Exception-Code is an error, and the IPv4 push-down retries in
+    text mode only when IPv4StringToNum itself failed (not on auth / network errors, which would double the scan)."""
+    class H(http.server.BaseHTTPRequestHandler):
+        def do_POST(self):
+            self.rfile.read(int(self.headers.get("Content-Length", 0)))
+            out = b"Code: 441. DB::Exception: Invalid IPv4 value"
+            self.send_response(200)
+            self.send_header("X-ClickHouse-Exception-Code", "441")
+            self.send_header("Content-Length", str(len(out)))
+            self.end_headers()
+            self.wfile.write(out)
+
+        def log_message(self, *a):
+            pass
+
+    srv = http.server.HTTPServer(("127.0.0.1", 0), H)
+    threading.Thread(target=srv.serve_forever, daemon=True).start()
+    try:
+        ch = ad.ClickHouseHTTP("jdbc:clickhouse://127.0.0.1:%d" % srv.server_address[1])
+        with pytest.raises(ad.ClickHouseError) as ei:
+            ch.select_native("SELECT 1")
+        assert ei.value.code == 441 and ad._is_ipv4_pushdown_failure(ei.value)
+    finally:
+        srv.shutdown()
+    assert not ad._is_ipv4_pushdown_failure(ConnectionRefusedError("nope"))
+    assert not ad._is_ipv4_pushdown_failure(ad.ClickHouseError(516, "Authentication failed"))
+
+    class T(_FakeTransport):
+        def select_native(self, q):
+            self.selects.append(q)
+            raise ad.ClickHouseError(516, "default: Authentication failed")
+
+    monkeypatch.setenv("TAD_IPV4_PUSHDOWN", "1")
+    tr = T(b"")
+    with pytest.raises(ad.ClickHouseError):
+        ad.main(["--algo", "EWMA", "--id", "p"], engine=_RecordingEngine(), transport=tr)
+    assert len(tr.selects) == 1                       # no second scan
+
+
+def test_null_stddev_goes_into_the_block_as_the_column_default():
+    """a single-point series has stddev_samp NULL; throughputStandardDeviation is a non-nullable Float64, the
+    reference's NULL lands there as 0."""
+    plan = ad.plan_query()
+    dicts = {slot: ad.Dictionary() for slot in ad.KEY_SLOTS}
+    got = {"src_ip": np.array([1, 2], np.uint32), "dst_ip": np.array([3, 4], np.uint32), "src_port": np.array([5, 6], np.uint16),
+           "dst_port": np.array([7, 8], np.uint16), "proto": np.array([6, 6], np.uint8), "flow_start": np.array([100, 100], np.uint32),
+           "flow_end": np.array([200, 201], np.uint32), "stddev": np.array([np.nan, 2.5]), "algo_calc": np.array([0.0, 0.0]),
+           "throughput": np.array([3.0, 3.0]), "anomaly": np.array([1, 1], np.uint8)}
+    a = chn.read_native(chn.tadetector_block_from_result(got, plan, dicts, "DBSCAN", "t"))
+    b = chn.read_native(chn.tadetector_block(ad._result_rows(got, plan, dicts, "DBSCAN", "t", None)))
+    assert a["throughputStandardDeviation"].tolist() == [0.0, 2.5] == b["throughputStandardDeviation"].tolist()

@@ -284,17 +284,17 @@ def _host_mask(flows: dict, plan: QueryPlan, branch: Branch, pod_label, pod_name
 
 def anomaly_detection(engine, algo_type: str, flows: dict, start_time: str = "", end_time: str = "", tad_id: str = "",
                       ns_ignore_list=(), agg_flow=None, pod_label=None, external_ip=None, svc_port_name=None,
-                      pod_name=None, pod_namespace=None, now=None):
+                      pod_name=None, pod_namespace=None, now=None, on_job=None):
     """anomaly_detection.py:647-710 + write_anomaly_detection_result (:713-726): returns the list of row dicts the
     reference appends to default.tadetector (one sentinel row when nothing is anomalous) and the job status."""
     got, st, plan, dicts = run_engine(engine, algo_type, flows, start_time, end_time, tad_id, ns_ignore_list, agg_flow, pod_label,
-                                      external_ip, svc_port_name, pod_name, pod_namespace)
+                                      external_ip, svc_port_name, pod_name, pod_namespace, on_job=on_job)
     return _result_rows(got, plan, dicts, algo_type, tad_id, pod_label, now), st
 
 
 def run_engine(engine, algo_type: str, flows: dict, start_time: str = "", end_time: str = "", tad_id: str = "",
                ns_ignore_list=(), agg_flow=None, pod_label=None, external_ip=None, svc_port_name=None,
-               pod_name=None, pod_namespace=None):
+               pod_name=None, pod_namespace=None, on_job=None):
     """Everything of :func:`anomaly_detection` up to the engine's result arrays: (result SoA, status, plan, dictionaries).
     The job entry point builds its INSERT body from these column-wise instead of materialising a dict per row."""
     if algo_type not in VALID_ALGOS:
@@ -340,8 +340,9 @@ def run_engine(engine, algo_type: str, flows: dict, start_time: str = "", end_ti
     # (_host_mask, or already by the WHERE clause of the SELECT the job entry sends) and must not reach the GPU, whose
     # absent flow_start column reads as 0.
     start = _epoch(plan.start_time) if table.get("flow_start") is not None else 0
+    kw = {} if on_job is None else {"on_job": on_job}      # progress hook of the controller (tad_poll while the job runs)
     got, st = engine.run(table, algo=algo_type, reducer=plan.reducer, start_time=start,
-                         end_time=_epoch(plan.end_time), tad_id=tad_id, ns_ignore=ignore_ids)
+                         end_time=_epoch(plan.end_time), tad_id=tad_id, ns_ignore=ignore_ids, **kw)
     return got, st, plan, dicts
 
 
@@ -447,6 +448,31 @@ def timed_job(engine, *args, **kw):
 logger = logging.getLogger("anomaly_detection")
 
 
+class ClickHouseError(RuntimeError):
+    """A query ClickHouse rejected (exception code + the server's text)."""
+
+    def __init__(self, code: int, text: str):
+        super().__init__("ClickHouse exception %d: %s" % (code, text))
+        self.code, self.text = code, text
+
+
+def _is_ipv4_pushdown_failure(e: Exception) -> bool:
+    """Only a failure of IPv4StringToNum itself (a non-IPv4 address in the table) justifies the second, text-mode scan;
+    authentication, network and syntax errors must surface."""
+    import urllib.error
+    text = ""
+    if isinstance(e, ClickHouseError):
+        text = e.text
+    elif isinstance(e, urllib.error.HTTPError):
+        try:
+            text = e.read(2000).decode(errors="replace")
+        except Exception:
+            text = str(e)
+    else:
+        text = str(e) if "DB::Exception" in str(e) else ""
+    return any(k in text for k in ("IPv4StringToNum", "Invalid IPv4", "CANNOT_PARSE_IPV4", "Cannot parse IPv4", "Code: 441"))
+
+
 class ClickHouseHTTP:
     """ClickHouse over its HTTP interface.  The reference hands its JDBC URL to the ClickHouse JDBC driver
     (anomaly_detection.py:655-662, 720-726), which talks to that very HTTP port (8123 in the default URL, :730-731);
@@ -469,7 +495,9 @@ class ClickHouseHTTP:
     def _post(self, query: str, body: bytes = b"") -> bytes:
         import urllib.parse
         import urllib.request
-        params = {"query": query}
+        # wait_end_of_query: ClickHouse buffers the response and reports a failure as a non-200 status instead of appending
+        # an exception text to a 200 stream that would then be parsed as a column block
+        params = {"query": query, "wait_end_of_query": "1"}
         if self.database:
             params["database"] = self.database
         req = urllib.request.Request(self.base + "?" + urllib.parse.urlencode(params), data=body, method="POST")
@@ -478,7 +506,11 @@ class ClickHouseHTTP:
         if self.password:
             req.add_header("X-ClickHouse-Key", self.password)
         with urllib.request.urlopen(req, timeout=self.timeout) as resp:
-            return resp.read()
+            code = resp.headers.get("X-ClickHouse-Exception-Code")
+            body = resp.read()
+            if code not in (None, "", "0"):
+                raise ClickHouseError(int(code), body[:500].decode(errors="replace"))
+            return body
 
     def select_native(self, sql: str) -> bytes:
         return self._post(sql.rstrip() + " FORMAT Native")
@@ -549,8 +581,8 @@ def main(argv=None, engine=None, transport=None) -> int:
         sql = raw_select_sql(plan, a["pod_label"], a["pod_name"], a["pod_namespace"], ipv4_pushdown=pushdown)
         try:
             stream = transport.select_native(sql)
-        except Exception:
-            if not pushdown:
+        except Exception as e:
+            if not pushdown or not _is_ipv4_pushdown_failure(e):
                 raise
             logger.info("IPv4 push-down failed (non-IPv4 addresses?): reading the addresses as text")
             sql = raw_select_sql(plan, a["pod_label"], a["pod_name"], a["pod_namespace"])

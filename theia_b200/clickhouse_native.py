@@ -279,10 +279,20 @@ def tadetector_block(rows: list) -> bytes:
             vals = [str(r.get(name, "")) for r in rows]
         elif typ == "Float64":
             vals = np.asarray([float("nan") if r.get(name) is None else float(r.get(name, 0.0)) for r in rows], dtype=np.float64)
+            if name == "throughputStandardDeviation":
+                vals = _null_to_default(vals)
         else:
             vals = np.asarray([_as_int(r.get(name, 0)) for r in rows], dtype=_FIXED[typ])
         cols.append((name, typ, vals))
     return write_native(cols)
+
+
+def _null_to_default(stddev) -> np.ndarray:
+    """stddev_samp of a single point is SQL NULL (NaN in the engine's result).  The reference's JDBC append writes NULL
+    into the non-nullable Float64 column throughputStandardDeviation (create_table.sh:363-384), where it becomes the
+    column default 0 -- so that is what goes into the block, not NaN."""
+    a = np.asarray(stddev, dtype=np.float64)
+    return np.where(np.isfinite(a), a, 0.0)
 
 
 def _as_int(v) -> int:
@@ -339,7 +349,7 @@ def tadetector_block_from_result(got: dict, plan, dicts: dict, algo_type: str, t
         cols["protocolIdentifier"] = ("num", got["proto"], None)
         cols["flowStartSeconds"] = ("num", got["flow_start"], None)
     cols["flowEndSeconds"] = ("num", got["flow_end"], None)
-    cols["throughputStandardDeviation"] = ("num", got["stddev"], None)
+    cols["throughputStandardDeviation"] = ("num", _null_to_default(got["stddev"]), None)
     cols["algoCalc"] = ("num", got["algo_calc"], None)
     cols["throughput"] = ("num", got["throughput"], None)
     for name, v in (("aggType", agg_type), ("algoType", algo_type), ("anomaly", "true"), ("id", tad_id)):

@@ -10,6 +10,7 @@ FAILED, not retried), CompletedStages/TotalStages progress (controller.go:426-45
 from __future__ import annotations
 
 import re
+import threading
 import uuid
 from dataclasses import dataclass, field
 
@@ -112,20 +113,54 @@ def build_job_args(name: str, spec: TADSpec) -> dict:
     return args
 
 
+class _Run:
+    """One dispatched job: the thread that drives it (what the Spark operator's driver pod is to the reference) and the
+    engine job handle the controller polls for progress."""
+
+    def __init__(self, args, flows):
+        self.args, self.flows = args, flows
+        self.lock = threading.Lock()
+        self.handle = None            # engine Job while it is alive (set / cleared by the engine's on_job hook)
+        self.rows = self.status = self.error = None
+        self.done = threading.Event()
+        self.thread = None
+
+
 class AnomalyDetectorController:
-    """syncTADetector (controller.go:354-383) over an in-memory CR store; one GPU engine instead of the Spark operator."""
+    """syncTADetector (controller.go:354-383) over an in-memory CR store; one GPU engine instead of the Spark operator.
+
+    Like the reference, dispatch and observation are decoupled: the first sync validates and dispatches the job
+    (startJob, controller.go:499-523 -- here a thread that runs the job on the engine instead of a SparkApplication CR),
+    every later sync only OBSERVES it: while the job runs it reports RUNNING with the engine's completed / total stages
+    (updateProgress, controller.go:426-453, which scrapes the Spark UI; here tad_poll), and once it has ended it finishes
+    the CR (finishJob, controller.go:400-424).  One deviation, on purpose: on completion the stage counters are set to the
+    job's final n/n, where the reference keeps whatever its last RUNNING poll saw (controller_test.go:303-306: 3 of 5)."""
 
     def __init__(self, engine):
         self.engine = engine
         self.crs: dict = {}          # name -> (spec, status)
-        self._jobs: dict = {}        # name -> (Job, Columns, args)
+        self._jobs: dict = {}        # name -> _Run
         self.results: dict = {}      # id -> tadetector rows (stands in for the ClickHouse table)
 
     def create(self, name: str, spec: TADSpec):
         self.crs[name] = (spec, TADStatus(state=""))
 
-    def sync(self, name: str, flows: dict | None = None) -> TADStatus:
+    def _drive(self, run: _Run):
         from . import anomaly_detection as job
+
+        def on_job(handle):          # called by the engine right after tad_submit, and with None before tad_release
+            with run.lock:
+                run.handle = handle
+        try:
+            run.rows, run.status = job.anomaly_detection(self.engine, flows=run.flows, on_job=on_job, **run.args)
+        except Exception as e:       # the job's failure is the CR's failure (controller.go:455-497)
+            run.error = str(e)
+        finally:
+            with run.lock:
+                run.handle = None
+            run.done.set()
+
+    def sync(self, name: str, flows: dict | None = None) -> TADStatus:
         spec, st = self.crs[name]
         if st.state in ("", STATE_NEW):                               # startJob, controller.go:499-523
             try:
@@ -134,20 +169,46 @@ class AnomalyDetectorController:
                 st.state, st.errorMsg = STATE_FAILED, "error in creating AnomalyDetector: %s" % e
                 return st
             st.state, st.sparkApplication = STATE_SCHEDULED, args["tad_id"]
-            self._jobs[name] = (args, flows)
+            run = self._jobs[name] = _Run(args, flows)
+            run.thread = threading.Thread(target=self._drive, args=(run,), daemon=True)
+            run.thread.start()
         elif st.state in (STATE_SCHEDULED, STATE_RUNNING):            # checkSparkApplicationStatus / updateProgress
-            args, fl = self._jobs[name]
-            rows, jst = job.anomaly_detection(self.engine, flows=fl, **args)
-            st.completedStages, st.totalStages = jst["completed_stages"], jst["total_stages"]
-            if jst["state"] == "COMPLETED":
-                self.results[args["tad_id"]] = rows
-                st.state = STATE_COMPLETED                            # finishJob, controller.go:400-424
+            run = self._jobs[name]
+            if not run.done.is_set():
+                with run.lock:
+                    p = run.handle.poll() if run.handle is not None else None
+                if p is not None and p["state"] in ("RUNNING", "COMPLETED"):
+                    st.state = STATE_RUNNING
+                    st.completedStages, st.totalStages = p["completed_stages"], p["total_stages"]
+                return st
+            if run.error is not None or run.status["state"] != "COMPLETED":
+                st.state, st.errorMsg = STATE_FAILED, run.error if run.error is not None else run.status["err_msg"]
             else:
-                st.state, st.errorMsg = STATE_FAILED, jst["err_msg"]
+                st.completedStages, st.totalStages = run.status["completed_stages"], run.status["total_stages"]
+                self.results[run.args["tad_id"]] = run.rows
+                st.state = STATE_COMPLETED                            # finishJob, controller.go:400-424
         return st
 
+    def wait(self, name: str, timeout: float = 600.0, observe=None) -> TADStatus:
+        """Poll sync() until the CR is terminal (the informer's resync loop); ``observe`` sees every status."""
+        import time
+        t0 = time.time()
+        while True:
+            st = self.sync(name)
+            if observe is not None:
+                observe(st)
+            if st.state in (STATE_COMPLETED, STATE_FAILED) or time.time() - t0 > timeout:
+                return st
+            self._jobs[name].done.wait(0.0005)
+
     def delete(self, name: str):
-        """cleanupTADetector (controller.go:385-398): drop the job and its rows (ALTER TABLE ... DELETE WHERE id)."""
+        """cleanupTADetector (controller.go:385-398): cancel a job that is still running (DeleteSparkApplication), then drop
+        it and its rows (ALTER TABLE ... DELETE WHERE id)."""
         spec, st = self.crs.pop(name)
-        self._jobs.pop(name, None)
+        run = self._jobs.pop(name, None)
+        if run is not None and not run.done.is_set():
+            with run.lock:
+                if run.handle is not None:
+                    run.handle.cancel()
+            run.done.wait(60)
         self.results.pop(st.sparkApplication, None)

@@ -14,6 +14,10 @@
 #include <thread>
 #include <vector>
 
+#include <sched.h>
+#include <sys/syscall.h>
+#include <unistd.h>
+
 #include "../../include/theia_tad.h"
 #include "tad_kernels.h"
 #include "tad_nccl.h"
@@ -37,6 +41,89 @@ constexpr int kMaxChunks = 16;          // host-resident input is copied and his
 constexpr int kMaxRanks = 8;
 constexpr int kMaxXChunks = kMaxSeg / kMaxRanks;   // exchange chunks: scatter of chunk c+1 overlaps the all-to-all of chunk c
 constexpr int kTotalStages = 6;   // ingest, partition, exchange, group, detect, egress
+
+// ---- NUMA placement of pinned host memory --------------------------------------------------------------------------
+// On a two-socket box half of the GPUs hang off each socket; a pinned buffer on the wrong socket makes every H2D / D2H
+// copy cross the inter-socket link, and eight ranks doing that at once is what held the 8-GPU end-to-end rate down in
+// round 1.  Pinned allocations therefore happen with the calling thread temporarily confined to the CPUs of the GPU's
+// NUMA node (the driver touches the pages inside cudaHostAlloc: first touch = local), with a PREFERRED memory policy on
+// top where the container allows set_mempolicy.  TAD_NUMA=0 switches all of it off.
+struct NumaInfo {
+    int node = -1;
+    cpu_set_t cpus;
+    bool ok = false;
+};
+
+NumaInfo numa_of_device(int device)
+{
+    NumaInfo ni;
+    CPU_ZERO(&ni.cpus);
+    if (const char *e = getenv("TAD_NUMA")) if (atoi(e) == 0) return ni;
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof(bus), device) != cudaSuccess) { cudaGetLastError(); return ni; }
+    for (char *p = bus; *p; p++) if (*p >= 'A' && *p <= 'Z') *p = (char)(*p - 'A' + 'a');
+    char path[128];
+    snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bus);
+    FILE *f = fopen(path, "r");
+    if (!f) return ni;
+    int node = -1;
+    if (fscanf(f, "%d", &node) != 1) node = -1;
+    fclose(f);
+    if (node < 0) return ni;
+    snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/cpulist", node);
+    f = fopen(path, "r");
+    if (!f) return ni;
+    char list[4096] = {0};
+    if (!fgets(list, sizeof(list), f)) list[0] = 0;
+    fclose(f);
+    int n = 0;
+    for (char *p = list; *p && *p != '\n';) {          // "0-31,64-95"
+        char *end = nullptr;
+        long a = strtol(p, &end, 10), b = a;
+        if (end == p) break;
+        if (*end == '-') { p = end + 1; b = strtol(p, &end, 10); }
+        for (long c = a; c <= b && c < CPU_SETSIZE; c++) { CPU_SET((int)c, &ni.cpus); n++; }
+        p = *end == ',' ? end + 1 : end;
+    }
+    // only CPUs this process may use anyway
+    cpu_set_t allowed;
+    if (sched_getaffinity(0, sizeof(allowed), &allowed) == 0) {
+        n = 0;
+        for (int c = 0; c < CPU_SETSIZE; c++) {
+            if (CPU_ISSET(c, &ni.cpus) && !CPU_ISSET(c, &allowed)) CPU_CLR(c, &ni.cpus);
+            if (CPU_ISSET(c, &ni.cpus)) n++;
+        }
+    }
+    ni.node = node;
+    ni.ok = n > 0;
+    return ni;
+}
+
+// Scope guard: the calling thread runs on (and prefers memory of) the GPU's NUMA node while it is alive.
+struct NumaScope {
+    cpu_set_t saved;
+    bool restore = false, policy = false;
+    explicit NumaScope(const NumaInfo &ni)
+    {
+        if (!ni.ok) return;
+        if (sched_getaffinity(0, sizeof(saved), &saved) != 0) return;
+        if (sched_setaffinity(0, sizeof(ni.cpus), &ni.cpus) == 0) restore = true;
+#ifdef SYS_set_mempolicy
+        unsigned long mask[16] = {0};
+        if (ni.node < (int)(sizeof(mask) * 8)) {
+            mask[ni.node / (8 * sizeof(unsigned long))] |= 1ul << (ni.node % (8 * sizeof(unsigned long)));
+            policy = syscall(SYS_set_mempolicy, 1 /* MPOL_PREFERRED */, mask, sizeof(mask) * 8) == 0;
+        }
+#endif
+    }
+    ~NumaScope()
+    {
+#ifdef SYS_set_mempolicy
+        if (policy) syscall(SYS_set_mempolicy, 0 /* MPOL_DEFAULT */, nullptr, 0);
+#endif
+        if (restore) sched_setaffinity(0, sizeof(saved), &saved);
+    }
+};
 
 double now_ms()
 {
@@ -88,6 +175,7 @@ struct tad_ctx {
     std::mutex pool_mu;
     std::vector<PinnedBlock> pinned_pool;
     NcclComm nccl;
+    NumaInfo numa;                                  // NUMA node of the GPU: pinned buffers and the worker thread live there
     // multi-GPU optimistic partition + peer pull: every rank scatters into fixed-capacity slots of an
     // exported buffer (arrival counters in front, slots behind), the peers map it (CUDA IPC) and the owner's group kernel
     // pulls its bucket segments over NVLink -- no histogram pass, no all-to-all, no receive buffer.
@@ -160,6 +248,7 @@ PinnedBlock take_pinned(tad_ctx *ctx, size_t bytes)
     }
     PinnedBlock b;
     b.cap = (bytes + bytes / 8 + 4095) & ~size_t(4095);
+    NumaScope numa(ctx->numa);
     CU(cudaHostAlloc(&b.p, b.cap, cudaHostAllocDefault));
     return b;
 }
@@ -831,6 +920,7 @@ void run_job(tad_ctx *ctx, tad_job *job)
 
 void worker_main(tad_ctx *ctx)
 {
+    if (ctx->numa.ok) sched_setaffinity(0, sizeof(ctx->numa.cpus), &ctx->numa.cpus);      // this thread only
     cudaSetDevice(ctx->cfg.device);
     for (;;) {
         tad_job *job = nullptr;
@@ -941,6 +1031,8 @@ int tad_init(const tad_config *cfg, tad_ctx **out)
     if (const char *e = getenv("TAD_DEBUG_LOGB")) ctx->debug_logb = atoi(e);
     if (const char *e = getenv("TAD_GROUP_TARGET")) ctx->debug_target = atoi(e);
     cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, cfg->device);
+    ctx->numa = numa_of_device(cfg->device);
+    NumaScope numa_scope(ctx->numa);
     bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
     for (int i = 0; ok && i < kMaxChunks; i++) ok = cudaEventCreateWithFlags(&ctx->chunk_ev[i], cudaEventDisableTiming) == cudaSuccess;
@@ -1019,6 +1111,7 @@ int tad_alloc_columns(tad_ctx *ctx, uint64_t capacity, int32_t mem, tad_columns 
     cols->capacity = capacity;
     cols->mem = mem;
     if (cudaSetDevice(ctx->cfg.device) != cudaSuccess) return TAD_ERR_CUDA;
+    NumaScope numa_scope(ctx->numa);
     void **slots[8] = {(void **)&cols->src_ip, (void **)&cols->dst_ip, (void **)&cols->src_port, (void **)&cols->dst_port,
                        (void **)&cols->proto, (void **)&cols->flow_start, (void **)&cols->flow_end, (void **)&cols->value};
     for (int i = 0; i < 8; i++) {
@@ -1037,6 +1130,7 @@ int tad_alloc_ns_columns(tad_ctx *ctx, tad_columns *cols)
 {
     if (!ctx || !cols || !cols->capacity) return TAD_ERR_INVALID_ARG;
     if (cudaSetDevice(ctx->cfg.device) != cudaSuccess) return TAD_ERR_CUDA;
+    NumaScope numa_scope(ctx->numa);
     void **slots[2] = {(void **)&cols->src_ns, (void **)&cols->dst_ns};
     for (int i = 0; i < 2; i++) {
         if (*slots[i]) continue;

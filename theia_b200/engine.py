@@ -199,14 +199,19 @@ class TadEngine:
             raise TadError(rc, msg)
         return job
 
-    def run(self, table: dict, **kw):
-        """Convenience: numpy table in, (result dict, status dict) out."""
+    def run(self, table: dict, on_job=None, **kw):
+        """Convenience: numpy table in, (result dict, status dict) out.  ``on_job(job)`` is called right after tad_submit
+        (the caller may poll it from another thread) and ``on_job(None)`` before the handle is released."""
         cols = self.columns_from_numpy(table)
         job = self.submit(cols, **kw)
+        if on_job is not None:
+            on_job(job)
         try:
             st = job.wait()
             return job.result(), st
         finally:
+            if on_job is not None:
+                on_job(None)
             job.release()
             cols.free()
 
