@@ -18,6 +18,11 @@ done; done
 TAD_DEBUG_LOGB=10 TAD_OPTIMISTIC=0 timeout 90 python bench.py --no-cpu --no-e2e --steps 3 > gpurun_out/ab_logb10.json 2> gpurun_out/ab_logb10.err
 TAD_OPTIMISTIC=0 $B > gpurun_out/ab_exact.json 2> gpurun_out/ab_exact.err
 TAD_DETECT_STAGED=0 $B > gpurun_out/ab_unstaged.json 2> gpurun_out/ab_unstaged.err
+TAD_DETECT_MODE=1 $B > gpurun_out/ab_direct.json 2> gpurun_out/ab_direct.err
+TAD_DETECT_MODE=1 timeout 300 python -m pytest tests/test_gpu_parity.py tests/test_gpu_full_size.py -m gpu -x -q > gpurun_out/ab_tests_direct.log 2>&1; echo "rc=$?" >> gpurun_out/ab_tests_direct.log
+tail -3 gpurun_out/ab_tests_direct.log
+(cd profiles/microbench && nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o scatter_tma scatter_tma.cu && timeout 60 ./scatter_tma) > gpurun_out/scatter_tma.log 2>&1
+tail -15 gpurun_out/scatter_tma.log
 python - <<'PY'
 import json, glob
 for p in sorted(glob.glob("gpurun_out/ab_*.json")):

@@ -772,7 +772,7 @@ void run_job(tad_ctx *ctx, tad_job *job)
 
     // ---- group ------------------------------------------------------------------------------
     const uint64_t cap_rows = owned ? owned : 1;
-    ensure(ctx->csr_v, cap_rows * 8);
+    ensure(ctx->csr_v, cap_rows * 8 + 64);       // + one sector: the direct detector reads whole 32-byte sectors
     ensure(ctx->csr_t, cap_rows * 4);
     uint64_t *csr_v = (uint64_t *)ctx->csr_v.p;
     uint32_t *csr_t = (uint32_t *)ctx->csr_t.p;

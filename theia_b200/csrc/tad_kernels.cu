@@ -1041,6 +1041,188 @@ __global__ void __launch_bounds__(NT) detect_ewma_kernel(const SeriesEntry *__re
 }
 
 // ----------------------------------------------------------------------------------------
+// K4, direct variant: no shared-memory stage.  A thread streams its own series straight out of csr_v, one full
+// 32-byte sector (four values, two 128-bit loads through the read-only path) per step with the next sector already
+// in flight, so nothing is fetched twice and the kernel runs at register-limited occupancy (5 CTAs of 128 threads
+// per SM instead of two of 96): the FP64 chains of ~600 threads per SM hide the memory latency that the staged
+// variant pays CTA by CTA.  Sectors are addressed from the sector-aligned start of the series (csr_v is padded by
+// one sector), elements outside [0, n) are masked.  The EWMA pass is warp-synchronous (queue slots from one ballot).
+// ----------------------------------------------------------------------------------------
+constexpr int kDirectThreads = 128;
+constexpr int kDirectQueue = 2048;                    // queued result rows per CTA (16 per series; the bench table has ~9)
+
+struct DirectSmem {
+    double qcalc[kDirectQueue];
+    uint32_t qpos[kDirectQueue];
+    uint32_t qmeta[kDirectQueue];                     // bit 31: flag, bits 30..16: owning thread
+    unsigned long long ent_a[kDirectThreads], ent_b[kDirectThreads];
+    double ent_sd[kDirectThreads];
+    uint32_t ent_proto[kDirectThreads];
+    uint32_t base, b0;
+    uint32_t wq[kDirectThreads / 32], wpre[kDirectThreads / 32];
+    uint32_t win[kBucketWindow + 1], woff[kBucketWindow + 1];
+};
+
+__device__ __forceinline__ ulonglong2 ldg_nc_u64x2(const uint64_t *p)
+{
+    ulonglong2 r;
+    asm volatile("ld.global.nc.v2.u64 {%0,%1}, [%2];" : "=l"(r.x), "=l"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint32_t ldg_nc_u32(const uint32_t *p)
+{
+    uint32_t r;
+    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ unsigned long long ldg_nc_u64(const uint64_t *p)
+{
+    unsigned long long r;
+    asm volatile("ld.global.nc.u64 %0, [%1];" : "=l"(r) : "l"(p));
+    return r;
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT, 5) detect_ewma_direct_kernel(const SeriesEntry *__restrict__ entries, const uint32_t *__restrict__ offsets,
+                                                                   const uint32_t *__restrict__ sbase, uint32_t B, uint32_t S,
+                                                                   const uint64_t *__restrict__ csr_v, const uint32_t *__restrict__ csr_t,
+                                                                   OutCols out, uint32_t out_cap, uint32_t *__restrict__ stats, int emit_all)
+{
+    __shared__ DirectSmem sm;
+    const uint32_t i = blockIdx.x * NT + threadIdx.x;
+    SeriesEntry e;
+    e.n = 0; e.off = 0; e.a = 0; e.b = 0; e.proto = 0;
+    const uint32_t bkt = find_bucket_cta(sbase, offsets, B, i < S ? i : S - 1, blockIdx.x * NT, sm.win, sm.woff, &sm.b0);
+    if (i < S) {
+        const uint32_t wk = bkt - sm.b0;
+        const bool inwin = wk < (uint32_t)kBucketWindow;
+        const uint32_t ob = inwin ? sm.woff[wk] : offsets[bkt], sb = inwin ? sm.win[wk] : sbase[bkt];
+        const uint4 *p = reinterpret_cast<const uint4 *>(entries + ob + (i - sb));
+        const uint4 k = p[0], w = p[1];
+        e.a = pack64(k.x, k.y); e.b = pack64(k.z, k.w); e.proto = w.x; e.n = w.y; e.off = w.z;
+    }
+    const uint32_t n = e.n;
+    const int mis = (int)(e.off & 3u);
+    const uint64_t *vs = csr_v + (e.off & ~3u);                   // sector-aligned start of the series
+    const uint32_t ng = n ? ((uint32_t)mis + n + 3u) >> 2 : 0u;   // sectors the series touches
+
+    // ---- pass 1: stddev_samp (Welford in time order; see series_stddev for the exact-division argument) -------------
+    bool has_sd = false;
+    double sd = 0.0;
+    if (n) {
+        double cnt = 0.0, avg = 0.0, m2 = 0.0;
+        ulonglong2 a = ldg_nc_u64x2(vs), b = ldg_nc_u64x2(vs + 2);
+        for (uint32_t g = 0; g < ng; g++) {
+            ulonglong2 na = a, nb = b;
+            if (g + 1 < ng) { na = ldg_nc_u64x2(vs + 4 * (g + 1)); nb = ldg_nc_u64x2(vs + 4 * (g + 1) + 2); }
+            const int i0 = (int)(4 * g) - mis;                    // element index of the sector's first value
+            const unsigned long long raw[4] = {a.x, a.y, b.x, b.y};
+            double rc[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) rc[j] = g_rcp[min((uint32_t)max(i0 + j + 1, 0), kRcpTable)];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int idx = i0 + j;
+                if (idx >= 0 && idx < (int)n) {
+                    const double x = __ull2double_rn(raw[j]);
+                    cnt = __dadd_rn(cnt, 1.0);
+                    const double d = __dsub_rn(x, avg);
+                    double dn;
+                    if ((uint32_t)idx + 1u <= kRcpTable) {
+                        const double q0 = __dmul_rn(d, rc[j]);
+                        dn = __fma_rn(__fma_rn(-cnt, q0, d), rc[j], q0);
+                    } else {
+                        dn = __ddiv_rn(d, cnt);
+                    }
+                    avg = __dadd_rn(avg, dn);
+                    m2 = __dadd_rn(m2, __dmul_rn(d, __dsub_rn(d, dn)));
+                }
+            }
+            a = na; b = nb;
+        }
+        has_sd = n >= 2;
+        sd = has_sd ? __dsqrt_rn(__ddiv_rn(m2, __dsub_rn(cnt, 1.0))) : __longlong_as_double(0x7ff8000000000000LL);
+        sm.ent_a[threadIdx.x] = e.a; sm.ent_b[threadIdx.x] = e.b; sm.ent_proto[threadIdx.x] = e.proto;
+        sm.ent_sd[threadIdx.x] = sd;
+    }
+
+    // ---- pass 2: EWMA + flag, warp-synchronous --------------------------------------------------------------------
+    constexpr uint32_t kWarps = NT / 32, kWarpQueue = kDirectQueue / kWarps;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t wbase = warp * kWarpQueue;
+    const uint32_t n_act = (n && (has_sd || emit_all)) ? n : 0u;
+    const uint32_t ng_act = n_act ? ng : 0u;
+    const uint32_t ng_max = __reduce_max_sync(0xffffffffu, ng_act);
+    uint32_t wcount = 0;
+    double prev = 0.0;
+    ulonglong2 a = make_ulonglong2(0ull, 0ull), b = a;
+    if (ng_act) { a = ldg_nc_u64x2(vs); b = ldg_nc_u64x2(vs + 2); }
+    for (uint32_t g = 0; g < ng_max; g++) {
+        ulonglong2 na = a, nb = b;
+        if (g + 1 < ng_act) { na = ldg_nc_u64x2(vs + 4 * (g + 1)); nb = ldg_nc_u64x2(vs + 4 * (g + 1) + 2); }
+        const int i0 = (int)(4 * g) - mis;
+        const unsigned long long raw[4] = {a.x, a.y, b.x, b.y};
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int idx = i0 + j;
+            const bool act = g < ng_act && idx >= 0 && idx < (int)n_act;
+            const double x = __ull2double_rn(raw[j]);
+            if (act) prev = __dadd_rn(__dmul_rn(0.5, prev), __dmul_rn(0.5, x));
+            const bool flag = act && has_sd && (fabs(__dsub_rn(x, prev)) > sd);
+            const bool push = act && (flag || emit_all);
+            const uint32_t mask = __ballot_sync(0xffffffffu, push);
+            if (mask == 0u) continue;
+            const uint32_t slot = wcount + (uint32_t)__popc(mask & ((1u << lane) - 1u));
+            wcount += (uint32_t)__popc(mask);
+            if (push) {
+                if (slot < kWarpQueue) {
+                    sm.qcalc[wbase + slot] = prev;
+                    sm.qpos[wbase + slot] = e.off + (uint32_t)idx;
+                    sm.qmeta[wbase + slot] = (flag ? 0x80000000u : 0u) | (threadIdx.x << 16);
+                } else {                                            // region full: direct emission
+                    const uint32_t o = atomicAdd(&stats[ST_OUTCOUNT], 1u);
+                    if (o < out_cap) write_out(out, o, e, csr_t[e.off + (uint32_t)idx], sd, prev, x, flag);
+                }
+            }
+        }
+        a = na; b = nb;
+    }
+    if (lane == 0) sm.wq[warp] = min(wcount, kWarpQueue);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t nq = 0;
+        for (uint32_t w = 0; w < kWarps; w++) { sm.wpre[w] = nq; nq += sm.wq[w]; }
+        sm.base = nq ? atomicAdd(&stats[ST_OUTCOUNT], nq) : 0u;
+    }
+    __syncthreads();
+    // ---- cooperative emission: one result row per thread and step, every column written coalesced; flowEndSeconds and
+    // throughput come through the read-only path, so the loads of a step are all in flight before its first store
+    for (uint32_t w = 0; w < kWarps; w++) {
+        const uint32_t cnt_w = sm.wq[w], out0 = sm.base + sm.wpre[w];
+        for (uint32_t k = threadIdx.x; k < cnt_w; k += NT) {
+            const uint32_t idx = out0 + k;
+            if (idx >= out_cap) continue;
+            const uint32_t j = w * kWarpQueue + k;
+            const uint32_t meta = sm.qmeta[j], pos = sm.qpos[j], owner = (meta >> 16) & 0x7fffu;
+            const uint32_t t = ldg_nc_u32(csr_t + pos);
+            const unsigned long long xv = ldg_nc_u64(csr_v + pos);
+            const uint64_t ka = sm.ent_a[owner], kb = sm.ent_b[owner];
+            out.src_ip[idx] = (uint32_t)(ka >> 32);
+            out.dst_ip[idx] = (uint32_t)ka;
+            out.flow_start[idx] = (uint32_t)(kb >> 32);
+            out.src_port[idx] = (uint16_t)(kb >> 16);
+            out.dst_port[idx] = (uint16_t)kb;
+            out.proto[idx] = (uint8_t)sm.ent_proto[owner];
+            out.flow_end[idx] = t;
+            out.stddev[idx] = sm.ent_sd[owner];
+            out.algo_calc[idx] = sm.qcalc[j];
+            out.throughput[idx] = __ull2double_rn(xv);
+            out.anomaly[idx] = (meta >> 31) ? 1 : 0;
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------
 // K4 (DBSCAN): exact 1-D rule of sklearn's DBSCAN(min_samples=4, eps=2.5e8)
 // (anomaly_detection.py:325-349; oracle/tad_oracle.py:calculate_dbscan_anomaly)
 // ----------------------------------------------------------------------------------------
@@ -1340,6 +1522,18 @@ cudaError_t launch_detect_ewma(cudaStream_t st, const SeriesEntry *entries, cons
         staged_s.store(staged, std::memory_order_release);
     }
     ensure_rcp_table(st);
+    static std::atomic<int> mode_s{-1};
+    int mode = mode_s.load(std::memory_order_acquire);
+    if (mode < 0) {
+        const char *ev = getenv("TAD_DETECT_MODE");          // 1 = direct (no stage, register-limited occupancy), 0 = TMA-staged
+        mode = ev ? atoi(ev) : 0;
+        mode_s.store(mode, std::memory_order_release);
+    }
+    if (mode == 1) {
+        detect_ewma_direct_kernel<kDirectThreads><<<(S + kDirectThreads - 1) / kDirectThreads, kDirectThreads, 0, st>>>(
+            entries, offsets, sbase, B, S, csr_v, csr_t, out, out_cap, stats, emit_all);
+        return cudaGetLastError();
+    }
     if (staged)
         detect_ewma_kernel<NT, true><<<(S + NT - 1) / NT, NT, sizeof(DetectSmem<true>), st>>>(entries, offsets, sbase, B, S, csr_v, csr_t,
                                                                                             out, out_cap, stats, emit_all);
