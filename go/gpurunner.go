@@ -24,11 +24,17 @@ import (
 
 // FlowColumns is what the ClickHouse reader hands over: one slice per selected column of default.flows
 // (create_table.sh:31-85), IPs already mapped to u32 (IPv4) or dictionary ids.
+//
+// FlowEnd and Throughput are required.  A key column the job's GROUP BY does not use is left nil (the aggregated-flow
+// modes use two or three of the six key slots, anomaly_detection.py:511-609): the engine then treats it as all zero.
+// Every non-nil slice must have len(FlowEnd) elements.  SrcNS / DstNS are namespace dictionary ids, needed only
+// together with JobSpec.NSIgnore.
 type FlowColumns struct {
 	SrcIP, DstIP, FlowStart, FlowEnd []uint32
 	SrcPort, DstPort                 []uint16
 	Proto                            []uint8
 	Throughput                       []uint64
+	SrcNS, DstNS                     []uint32
 }
 
 // JobSpec carries the already validated arguments startSparkApplication would have put into argv
@@ -36,9 +42,13 @@ type FlowColumns struct {
 type JobSpec struct {
 	Algo       string // EWMA | ARIMA | DBSCAN
 	SumReducer bool   // aggregated-flow modes use sum(throughput), per-connection mode max(throughput)
-	StartTime  uint32 // epoch seconds, 0 = unbounded
-	EndTime    uint32
-	ID         string
+	StartTime  uint32 // epoch seconds, 0 = unbounded; needs FlowColumns.FlowStart (a key column): the modes whose key has
+	// no flowStartSeconds (external, svc) apply the lower bound in their SELECT's WHERE clause and pass 0 here
+	EndTime  uint32
+	ID       string
+	NSIgnore []uint32 // --ns-ignore-list (controller.go:546), mapped to the namespace ids used in SrcNS / DstNS
+	// rows of the whole table over all ranks when the job runs on several GPUs (world_size > 1); 0 on one GPU
+	GlobalRows uint64
 }
 
 // AnomalyRow is one row of default.tadetector (create_table.sh:363-384) minus the per-job constants.
@@ -78,27 +88,73 @@ func algoCode(a string) C.int32_t {
 	return C.TAD_ALGO_EWMA
 }
 
+// fillColumn copies a Go slice into a library-owned pinned column, or -- for a key column the job does not use --
+// zero-fills it (an all-zero column and a NULL column group identically).  tad_alloc_columns does not zero its
+// buffers (cudaHostAlloc), so a short or missing slice must never leave part of a column unwritten: uninitialised
+// bytes would be hashed into the connection key.
+func fillColumn[T any](dst **T, src []T, n int, name string, required bool) error {
+	if src == nil && !required {
+		var zero T
+		C.memset(unsafe.Pointer(*dst), 0, C.size_t(uintptr(n)*unsafe.Sizeof(zero)))
+		return nil
+	}
+	if len(src) != n {
+		return fmt.Errorf("column %s has %d values, flowEndSeconds has %d", name, len(src), n)
+	}
+	copy(unsafe.Slice(*dst, n), src)
+	return nil
+}
+
 // Start replaces CreateSparkApplication (controller.go:685): non-blocking submit.
 func (r *gpuJobRunner) Start(spec JobSpec, in *FlowColumns) error {
 	n := len(in.FlowEnd)
+	if spec.StartTime != 0 && in.FlowStart == nil {
+		return illeagelArguementError{fmt.Errorf("invalid request: start_time needs the flow_start column")}
+	}
 	var cols C.tad_columns
 	if rc := C.tad_alloc_columns(r.ctx, C.uint64_t(n), C.TAD_MEM_HOST, &cols); rc != C.TAD_OK {
 		return fmt.Errorf("tad_alloc_columns: %s", C.GoString(C.tad_strerror(rc)))
 	}
+	fail := func(err error) error {
+		C.tad_free_columns(r.ctx, &cols)
+		return err
+	}
 	// library-owned pinned buffers: the engine never sees a Go pointer
-	copy(unsafe.Slice((*uint32)(unsafe.Pointer(cols.src_ip)), n), in.SrcIP)
-	copy(unsafe.Slice((*uint32)(unsafe.Pointer(cols.dst_ip)), n), in.DstIP)
-	copy(unsafe.Slice((*uint16)(unsafe.Pointer(cols.src_port)), n), in.SrcPort)
-	copy(unsafe.Slice((*uint16)(unsafe.Pointer(cols.dst_port)), n), in.DstPort)
-	copy(unsafe.Slice((*uint8)(unsafe.Pointer(cols.proto)), n), in.Proto)
-	copy(unsafe.Slice((*uint32)(unsafe.Pointer(cols.flow_start)), n), in.FlowStart)
-	copy(unsafe.Slice((*uint32)(unsafe.Pointer(cols.flow_end)), n), in.FlowEnd)
-	copy(unsafe.Slice((*uint64)(unsafe.Pointer(cols.value)), n), in.Throughput)
+	for _, err := range []error{
+		fillColumn((**uint32)(unsafe.Pointer(&cols.src_ip)), in.SrcIP, n, "sourceIP", false),
+		fillColumn((**uint32)(unsafe.Pointer(&cols.dst_ip)), in.DstIP, n, "destinationIP", false),
+		fillColumn((**uint16)(unsafe.Pointer(&cols.src_port)), in.SrcPort, n, "sourceTransportPort", false),
+		fillColumn((**uint16)(unsafe.Pointer(&cols.dst_port)), in.DstPort, n, "destinationTransportPort", false),
+		fillColumn((**uint8)(unsafe.Pointer(&cols.proto)), in.Proto, n, "protocolIdentifier", false),
+		fillColumn((**uint32)(unsafe.Pointer(&cols.flow_start)), in.FlowStart, n, "flowStartSeconds", false),
+		fillColumn((**uint32)(unsafe.Pointer(&cols.flow_end)), in.FlowEnd, n, "flowEndSeconds", true),
+		fillColumn((**uint64)(unsafe.Pointer(&cols.value)), in.Throughput, n, "throughput", true),
+	} {
+		if err != nil {
+			return fail(err)
+		}
+	}
 	cols.rows = C.uint64_t(n)
 
-	js := C.tad_job_spec{algo: algoCode(spec.Algo), start_time: C.uint32_t(spec.StartTime), end_time: C.uint32_t(spec.EndTime)}
+	js := C.tad_job_spec{algo: algoCode(spec.Algo), start_time: C.uint32_t(spec.StartTime), end_time: C.uint32_t(spec.EndTime),
+		global_rows: C.uint64_t(spec.GlobalRows)}
 	if spec.SumReducer {
 		js.reducer = C.TAD_REDUCE_SUM
+	}
+	if len(spec.NSIgnore) > 0 {
+		// namespace filter of the per-connection query (anomaly_detection.py:576-580): ids ride in two extra columns
+		if rc := C.tad_alloc_ns_columns(r.ctx, &cols); rc != C.TAD_OK {
+			return fail(fmt.Errorf("tad_alloc_ns_columns: %s", C.GoString(C.tad_strerror(rc))))
+		}
+		if err := fillColumn((**uint32)(unsafe.Pointer(&cols.src_ns)), in.SrcNS, n, "sourcePodNamespace", true); err != nil {
+			return fail(err)
+		}
+		if err := fillColumn((**uint32)(unsafe.Pointer(&cols.dst_ns)), in.DstNS, n, "destinationPodNamespace", true); err != nil {
+			return fail(err)
+		}
+		// tad_submit copies the list: the Go slice need not outlive the call (cgo pins it for its duration)
+		js.n_ns_ignore = C.uint32_t(len(spec.NSIgnore))
+		js.ns_ignore = (*C.uint32_t)(unsafe.Pointer(&spec.NSIgnore[0]))
 	}
 	cid := C.CString(spec.ID)
 	C.strncpy(&js.id[0], cid, 39)
