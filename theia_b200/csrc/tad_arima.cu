@@ -11,6 +11,7 @@
 // Compute-bound FP64 (about n^2/2 Kalman steps x ~100 likelihood evaluations per series), so the
 // mapping is one WARP per series with one lane per prefix fit; the series lives in L1.
 #include <cfloat>
+#include <cstdlib>
 
 #include "tad_kernels.h"
 
@@ -392,80 +393,127 @@ __host__ __device__ int dcsrch_step(LineSearch &ls, double &stp, double f, doubl
 }
 
 // ------------------------------------------------------------------------------------------
-// L-BFGS (the unconstrained path of L-BFGS-B 3.0 as SciPy drives it)
+// L-BFGS (the unconstrained path of L-BFGS-B 3.0 as SciPy drives it), written as a resumable state machine:
+// the caller evaluates (f, g) at x, lbfgs_advance() consumes them and either leaves the next trial point in x
+// (returns false) or ends the fit (returns true, x = the solution).  The host driver below loops over it; the fit
+// kernel lets all lanes of a warp evaluate TOGETHER (the Kalman-filter likelihood, >95 % of the work, then runs
+// converged) and only the cheap bookkeeping between two evaluations diverges.
 // ------------------------------------------------------------------------------------------
-__host__ __device__ void arima_fit(const ArimaObj &o, double x[3])
+struct Lbfgs {
+    double S[kLbfgsM][3], Y[kLbfgsM][3], rho[kLbfgsM];
+    int col, head, iter, ifun, state;        // state 0: first evaluation pending, 1: line-search evaluation pending
+    double theta, f, g[3], d[3], stp, fold, xold[3], gold[3], gdold, gd;
+    LineSearch ls;
+};
+
+__host__ __device__ __forceinline__ void lbfgs_init(Lbfgs &s)
+{
+    s.col = 0; s.head = 0; s.iter = 0; s.ifun = 0; s.state = 0; s.theta = 1.0;
+}
+
+// start iterations from (s.f, s.g) at x until a line search has its first trial point in x (false) or the fit ends (true)
+__host__ __device__ bool lbfgs_begin_iter(Lbfgs &s, double x[3])
+{
+    const double stpmx = 1e10, ftol = 1e-3;
+    for (;;) {
+        if (s.iter >= 50) return true;
+        // ---- direction d = -H g (two-loop recursion, H0 = I / theta) ------------------------
+        double d[3] = {s.g[0], s.g[1], s.g[2]}, alpha[kLbfgsM];
+        for (int k = s.col - 1; k >= 0; k--) {
+            const int i = (s.head + k) % kLbfgsM;
+            alpha[k] = s.rho[i] * (s.S[i][0] * d[0] + s.S[i][1] * d[1] + s.S[i][2] * d[2]);
+            for (int c = 0; c < 3; c++) d[c] -= alpha[k] * s.Y[i][c];
+        }
+        for (int c = 0; c < 3; c++) d[c] /= s.theta;
+        for (int k = 0; k < s.col; k++) {
+            const int i = (s.head + k) % kLbfgsM;
+            const double beta = s.rho[i] * (s.Y[i][0] * d[0] + s.Y[i][1] * d[1] + s.Y[i][2] * d[2]);
+            for (int c = 0; c < 3; c++) d[c] += s.S[i][c] * (alpha[k] - beta);
+        }
+        for (int c = 0; c < 3; c++) s.d[c] = -d[c];
+        // ---- line search ----------------------------------------------------------------------
+        const double dnorm = sqrt(s.d[0] * s.d[0] + s.d[1] * s.d[1] + s.d[2] * s.d[2]);
+        s.stp = s.iter == 0 ? fmin(1.0 / dnorm, stpmx) : 1.0;
+        s.fold = s.f;
+        for (int c = 0; c < 3; c++) { s.xold[c] = x[c]; s.gold[c] = s.g[c]; }
+        s.gdold = s.g[0] * s.d[0] + s.g[1] * s.d[1] + s.g[2] * s.d[2];
+        s.gd = s.gdold;
+        const bool ok = s.gdold < 0.0 && isfinite(s.gdold) && dnorm > 0.0;
+        if (ok) {
+            dcsrch_start(s.ls, s.stp, s.f, s.gdold, ftol, 0.0, stpmx);
+            s.ifun = 0;
+            for (int c = 0; c < 3; c++) x[c] = s.xold[c] + s.stp * s.d[c];
+            s.state = 1;
+            return false;
+        }
+        // no descent direction: with stored pairs restart from steepest descent, else stop (x, f, g are unchanged)
+        if (s.col == 0) return true;
+        s.col = 0; s.head = 0; s.theta = 1.0;
+    }
+}
+
+__host__ __device__ bool lbfgs_advance(Lbfgs &s, double x[3], double f, const double g[3])
 {
     const double pgtol = 1e-8, factr = 1e2, epsmch = DBL_EPSILON, stpmx = 1e10;
     const double ftol = 1e-3, gtol = 0.9, xtol = 0.1;
-    double S[kLbfgsM][3], Y[kLbfgsM][3], rho[kLbfgsM];
-    int col = 0, head = 0;               // pairs stored in a ring: oldest at head
-    double theta = 1.0;
-    double f, g[3];
-    arima_fg(o, x, f, g);
-    if (fmax(fabs(g[0]), fmax(fabs(g[1]), fabs(g[2]))) <= pgtol) return;
-    for (int iter = 0; iter < 50;) {
-        // ---- direction d = -H g (two-loop recursion, H0 = I / theta) ------------------------
-        double d[3] = {g[0], g[1], g[2]}, alpha[kLbfgsM];
-        for (int k = col - 1; k >= 0; k--) {
-            const int i = (head + k) % kLbfgsM;
-            alpha[k] = rho[i] * (S[i][0] * d[0] + S[i][1] * d[1] + S[i][2] * d[2]);
-            for (int c = 0; c < 3; c++) d[c] -= alpha[k] * Y[i][c];
-        }
-        for (int c = 0; c < 3; c++) d[c] /= theta;
-        for (int k = 0; k < col; k++) {
-            const int i = (head + k) % kLbfgsM;
-            const double beta = rho[i] * (Y[i][0] * d[0] + Y[i][1] * d[1] + Y[i][2] * d[2]);
-            for (int c = 0; c < 3; c++) d[c] += S[i][c] * (alpha[k] - beta);
-        }
-        for (int c = 0; c < 3; c++) d[c] = -d[c];
-        // ---- line search ----------------------------------------------------------------------
-        const double dnorm = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
-        double stp = iter == 0 ? fmin(1.0 / dnorm, stpmx) : 1.0;
-        const double fold = f, xold[3] = {x[0], x[1], x[2]}, gold[3] = {g[0], g[1], g[2]};
-        const double gdold = g[0] * d[0] + g[1] * d[1] + g[2] * d[2];
-        bool ok = gdold < 0.0 && isfinite(gdold) && dnorm > 0.0;
-        double gd = gdold;
-        if (ok) {
-            LineSearch ls;
-            dcsrch_start(ls, stp, f, gdold, ftol, 0.0, stpmx);
-            int task = LS_FG, ifun = 0;
-            while (task == LS_FG) {
-                if (ifun >= 20) { ok = false; break; }
-                for (int c = 0; c < 3; c++) x[c] = xold[c] + stp * d[c];
-                arima_fg(o, x, f, g);
-                ifun++;
-                gd = g[0] * d[0] + g[1] * d[1] + g[2] * d[2];
-                if (!isfinite(f) || !isfinite(gd)) { ok = false; break; }
-                task = dcsrch_step(ls, stp, f, gd, ftol, gtol, xtol, 0.0, stpmx);
+    s.f = f;
+    for (int c = 0; c < 3; c++) s.g[c] = g[c];
+    if (s.state == 0) {
+        if (fmax(fabs(g[0]), fmax(fabs(g[1]), fabs(g[2]))) <= pgtol) return true;
+        return lbfgs_begin_iter(s, x);
+    }
+    // ---- an evaluation of the running line search ---------------------------------------------
+    s.ifun++;
+    s.gd = g[0] * s.d[0] + g[1] * s.d[1] + g[2] * s.d[2];
+    bool ok = isfinite(f) && isfinite(s.gd);
+    if (ok) {
+        const int task = dcsrch_step(s.ls, s.stp, f, s.gd, ftol, gtol, xtol, 0.0, stpmx);
+        if (task == LS_FG) {
+            if (s.ifun >= 20) ok = false;
+            else {
+                for (int c = 0; c < 3; c++) x[c] = s.xold[c] + s.stp * s.d[c];
+                return false;
             }
         }
-        if (!ok) {
-            // line search failed: restore; with stored pairs restart from steepest descent, else stop
-            f = fold;
-            for (int c = 0; c < 3; c++) { x[c] = xold[c]; g[c] = gold[c]; }
-            if (col == 0) return;
-            col = 0; head = 0; theta = 1.0;
-            continue;
-        }
-        iter++;
-        if (fmax(fabs(g[0]), fmax(fabs(g[1]), fabs(g[2]))) <= pgtol) return;
-        const double ddum = fmax(fabs(fold), fmax(fabs(f), 1.0));
-        if (fold - f <= epsmch * factr * ddum) return;
-        // ---- update the limited-memory matrices ---------------------------------------------------
-        double r[3], s[3], rr = 0.0;
-        for (int c = 0; c < 3; c++) { r[c] = g[c] - gold[c]; s[c] = x[c] - xold[c]; rr += r[c] * r[c]; }
-        double dr, dd;
-        if (stp == 1.0) { dr = gd - gdold; dd = -gdold; }
-        else { dr = (gd - gdold) * stp; dd = -gdold * stp; }
-        if (dr > epsmch * dd) {
-            int slot;
-            if (col < kLbfgsM) { slot = (head + col) % kLbfgsM; col++; }
-            else { slot = head; head = (head + 1) % kLbfgsM; }
-            for (int c = 0; c < 3; c++) { S[slot][c] = s[c]; Y[slot][c] = r[c]; }
-            rho[slot] = 1.0 / dr;
-            theta = rr / dr;
-        }
+    }
+    if (!ok) {
+        // line search failed: restore; with stored pairs restart from steepest descent, else stop
+        s.f = s.fold;
+        for (int c = 0; c < 3; c++) { x[c] = s.xold[c]; s.g[c] = s.gold[c]; }
+        if (s.col == 0) return true;
+        s.col = 0; s.head = 0; s.theta = 1.0;
+        return lbfgs_begin_iter(s, x);
+    }
+    s.iter++;
+    if (fmax(fabs(g[0]), fmax(fabs(g[1]), fabs(g[2]))) <= pgtol) return true;
+    const double ddum = fmax(fabs(s.fold), fmax(fabs(f), 1.0));
+    if (s.fold - f <= epsmch * factr * ddum) return true;
+    // ---- update the limited-memory matrices ---------------------------------------------------
+    double r[3], sv[3], rr = 0.0;
+    for (int c = 0; c < 3; c++) { r[c] = g[c] - s.gold[c]; sv[c] = x[c] - s.xold[c]; rr += r[c] * r[c]; }
+    double dr, dd;
+    if (s.stp == 1.0) { dr = s.gd - s.gdold; dd = -s.gdold; }
+    else { dr = (s.gd - s.gdold) * s.stp; dd = -s.gdold * s.stp; }
+    if (dr > epsmch * dd) {
+        int slot;
+        if (s.col < kLbfgsM) { slot = (s.head + s.col) % kLbfgsM; s.col++; }
+        else { slot = s.head; s.head = (s.head + 1) % kLbfgsM; }
+        for (int c = 0; c < 3; c++) { s.S[slot][c] = sv[c]; s.Y[slot][c] = r[c]; }
+        s.rho[slot] = 1.0 / dr;
+        s.theta = rr / dr;
+    }
+    return lbfgs_begin_iter(s, x);
+}
+
+// one fit, evaluated and advanced in place (host tests; the sequential device path)
+__host__ __device__ void arima_fit(const ArimaObj &o, double x[3])
+{
+    Lbfgs s;
+    lbfgs_init(s);
+    for (;;) {
+        double f, g[3];
+        arima_fg(o, x, f, g);
+        if (lbfgs_advance(s, x, f, g)) return;
     }
 }
 
@@ -529,6 +577,60 @@ __global__ void __launch_bounds__(128) arima_fit_kernel(const SeriesEntry *__res
         arima_transform(u, phi, theta, s2);
         arima_loglike(o, phi, theta, s2, &fc);
         p[t] = fc;
+    }
+}
+
+// Evaluation-synchronous variant: one warp per series; the prefix fits t = n-1 .. 3 form a job list that the lanes
+// work through dynamically (longest first, so the fits in flight have similar lengths).  Every round, all lanes that
+// hold a job evaluate the objective and its forward-difference gradient TOGETHER -- the same Kalman-filter loop, each lane
+// on its own prefix and parameters -- then each lane advances its own optimiser state (lbfgs_advance) to the next trial
+// point; a lane whose fit has ended writes its forecast and takes the next job.  Per fit the arithmetic is the same as
+// in arima_fit: only the scheduling differs.
+__global__ void __launch_bounds__(128) arima_fit_sync_kernel(const SeriesEntry *__restrict__ entries, const uint32_t *__restrict__ offsets,
+                                                             const uint32_t *__restrict__ sbase, uint32_t B, uint32_t S,
+                                                             const double *__restrict__ yb, const double *__restrict__ lam,
+                                                             double *__restrict__ pred)
+{
+    const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    if (i >= S) return;                                    // warp-uniform
+    if (isnan(lam[i])) return;
+    const SeriesEntry e = load_entry(entries, offsets, sbase, B, i);
+    const double *y = yb + e.off;
+    double *p = pred + e.off;
+    for (uint32_t t = lane; t < min(e.n, 3u); t += 32) p[t] = y[t];      // train = first three points (:241,255)
+    int next = (int)e.n - 1;                               // next job to hand out (warp-uniform), down to 3
+    bool busy = false;
+    ArimaObj o{y, 0};
+    double u[3] = {0.0, 0.0, 0.0};
+    Lbfgs st;
+    for (;;) {
+        // ---- hand the next jobs to the idle lanes --------------------------------------------
+        const uint32_t idle = __ballot_sync(0xffffffffu, !busy);
+        if (idle && next >= 3) {
+            const int rank = __popc(idle & ((1u << lane) - 1u));
+            if (!busy && next - rank >= 3) {
+                o.n = (uint32_t)(next - rank);
+                arima_start(o, u);
+                lbfgs_init(st);
+                busy = true;
+            }
+            next -= __popc(idle);
+        }
+        if (!__any_sync(0xffffffffu, busy)) break;
+        // ---- all busy lanes evaluate together -------------------------------------------------
+        double f = 0.0, g[3] = {0.0, 0.0, 0.0};
+        if (busy) arima_fg(o, u, f, g);
+        __syncwarp();
+        // ---- every lane advances its own optimiser --------------------------------------------
+        if (busy && lbfgs_advance(st, u, f, g)) {
+            double phi, theta, s2, fc = 0.0;
+            arima_transform(u, phi, theta, s2);
+            arima_loglike(o, phi, theta, s2, &fc);
+            p[o.n] = fc;
+            busy = false;
+        }
+        __syncwarp();
     }
 }
 
@@ -637,8 +739,14 @@ cudaError_t launch_detect_arima(cudaStream_t st, const SeriesEntry *entries, con
     if (fit) {
         arima_boxcox_kernel<<<(S + 127) / 128, 128, 0, st>>>(entries, offsets, sbase, B, S, csr_v, scratch_y, scratch_lam);
         const uint64_t threads = (uint64_t)S * 32;
-        arima_fit_kernel<<<(uint32_t)((threads + 127) / 128), 128, 0, st>>>(entries, offsets, sbase, B, S, scratch_y, scratch_lam,
-                                                                           scratch_pred);
+        static int mode = -1;                      // TAD_ARIMA_MODE: 1 = evaluation-synchronous fits, 0 = one independent fit per lane
+        if (mode < 0) { const char *ev = getenv("TAD_ARIMA_MODE"); mode = ev ? atoi(ev) : 1; }
+        if (mode == 1)
+            arima_fit_sync_kernel<<<(uint32_t)((threads + 127) / 128), 128, 0, st>>>(entries, offsets, sbase, B, S, scratch_y,
+                                                                                    scratch_lam, scratch_pred);
+        else
+            arima_fit_kernel<<<(uint32_t)((threads + 127) / 128), 128, 0, st>>>(entries, offsets, sbase, B, S, scratch_y, scratch_lam,
+                                                                               scratch_pred);
     }
     constexpr int NT = 128;
     detect_arima_kernel<NT><<<(S + NT - 1) / NT, NT, 0, st>>>(entries, offsets, sbase, B, S, csr_v, csr_t, scratch_pred,
