@@ -180,6 +180,7 @@ struct tad_ctx {
     // exported buffer (arrival counters in front, slots behind), the peers map it (CUDA IPC) and the owner's group kernel
     // pulls its bucket segments over NVLink -- no histogram pass, no all-to-all, no receive buffer.
     int peer_pull = 1;                              // TAD_PEER_PULL=0: always the exact partition + NCCL all-to-all
+    size_t x_budget = 72ull << 30;                  // largest exported slot buffer (TAD_SLOT_BUDGET_GB); beyond it: exact partition
     DevBuf xbuf;                                    // exported: [counters: B x u32, padded][slots: B x slot x Row32]
     void *peer_x[kMaxRanks]{};                      // peers' xbuf mapped into this process
     bool peers_mapped = false;
@@ -443,6 +444,7 @@ void run_job(tad_ctx *ctx, tad_job *job)
         if (nccl_allgather(&ctx->nccl, d_small, d_small + 8, 8, st)) fail(TAD_ERR_NCCL, "%s", nccl_last_error());
         CU(cudaMemcpyAsync(ctx->h_small, d_small + 8, 8 * world, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
+        mark(TAD_PHASE_SYNC);          // arrival skew of the ranks at job start (avoided when the host passes global_rows)
         R_total = 0;
         for (int r = 0; r < world; r++) R_total += ctx->h_small[r];
     }
@@ -552,7 +554,7 @@ void run_job(tad_ctx *ctx, tad_job *job)
     const size_t x_need = x_cnt_bytes + (size_t)B * slotM * sizeof(Row32);
     bool sync_at_end = false;
     if (world > 1 && ctx->peer_pull && ctx->optimistic && R_total > 0 && (uint64_t)B * slotM <= (1ull << 31) &&
-        x_need <= (48ull << 30)) {
+        x_need <= ctx->x_budget) {
         auto gather16 = [&]() {        // blocking 128-byte all-gather through pinned memory (regrow only)
             CU(cudaMemcpyAsync(d_small, ctx->h_small, 16 * 8, cudaMemcpyHostToDevice, st));
             if (nccl_allgather(&ctx->nccl, d_small, d_small + 16, 16 * 8, st)) fail(TAD_ERR_NCCL, "%s", nccl_last_error());
@@ -1040,6 +1042,7 @@ int tad_init(const tad_config *cfg, tad_ctx **out)
     for (int i = 0; ok && i <= kMaxXChunks; i++) ok = cudaEventCreateWithFlags(&ctx->x_ev[i], cudaEventDisableTiming) == cudaSuccess;
     if (const char *e = getenv("TAD_OPTIMISTIC")) ctx->optimistic = atoi(e);
     if (const char *e = getenv("TAD_PEER_PULL")) ctx->peer_pull = atoi(e);
+    if (const char *e = getenv("TAD_SLOT_BUDGET_GB")) ctx->x_budget = (size_t)strtoull(e, nullptr, 10) << 30;
     if (const char *e = getenv("TAD_EXCHANGE_MIN_ROWS")) ctx->exchange_min_rows = strtoull(e, nullptr, 10);
     if (getenv("TAD_EXCHANGE_CHUNKS")) ctx->exchange_chunks_forced = true;
     if (const char *e = getenv("TAD_EXCHANGE_CHUNKS")) ctx->exchange_chunks = atoi(e) < 1 ? 1 : (atoi(e) > kMaxXChunks ? kMaxXChunks : atoi(e));
