@@ -27,36 +27,24 @@ namespace tad {
 // ----------------------------------------------------------------------------------------
 // small PTX helpers
 // ----------------------------------------------------------------------------------------
-// L2 eviction policy of the partition's streams (EXPERIMENT, TAD_SCATTER_LOADPOL / TAD_SCATTER_STOREPOL = 0 normal,
-// 1 evict_first, 2 evict_last): the input is read once (evict_first keeps it from displacing anything), a bucket's
-// 128-byte line receives its four rows over ~0.5 M rows of other traffic (evict_last should keep the partially
-// written line in L2 until it is complete, so that DRAM sees whole lines instead of single sectors).
-__device__ __forceinline__ uint64_t make_policy(int kind)
-{
-    uint64_t p;
-    if (kind == 1) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-    else if (kind == 2) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-    else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
-__device__ __forceinline__ uint4 ldg_stream128(const void *p, uint64_t pol)
+__device__ __forceinline__ uint4 ldg_stream128(const void *p)
 {
     uint4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
-                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(pol));
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
 }
-__device__ __forceinline__ uint2 ldg_stream64(const void *p, uint64_t pol)
+__device__ __forceinline__ uint2 ldg_stream64(const void *p)
 {
     uint2 r;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;" : "=r"(r.x), "=r"(r.y) : "l"(p), "l"(pol));
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
     return r;
 }
 // one 32-byte row = one 256-bit store = one full DRAM sector per request (sm_100: STG.E.256)
-__device__ __forceinline__ void stg256(void *p, uint4 lo, uint4 hi, uint64_t pol)
+__device__ __forceinline__ void stg256(void *p, uint4 lo, uint4 hi)
 {
-    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8}, %9;"
-                 :: "l"(p), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w), "l"(pol)
+    asm volatile("st.global.L1::no_allocate.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "l"(p), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w)
                  : "memory");
 }
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
@@ -100,20 +88,19 @@ struct OptScatter {
     uint32_t ovf_cap;
     Row32 *ovf;
     uint32_t *ovf_count;
-    int load_pol, store_pol;  // L2 eviction policy kinds (make_policy)
 };
 
-__device__ __forceinline__ void place_row(const RowRegs &r, uint32_t bucket, uint32_t pos, Row32 *part, const OptScatter &o, uint64_t spol)
+__device__ __forceinline__ void place_row(const RowRegs &r, uint32_t bucket, uint32_t pos, Row32 *part, const OptScatter &o)
 {
     const uint4 lo = make_uint4((uint32_t)r.a, (uint32_t)(r.a >> 32), (uint32_t)r.b, (uint32_t)(r.b >> 32));
     const uint4 hi = make_uint4((uint32_t)r.value, (uint32_t)(r.value >> 32), r.t, r.proto);
     if (o.cap == 0) {
-        stg256(part + pos, lo, hi, spol);
+        stg256(part + pos, lo, hi);
     } else if (pos < o.cap) {
-        stg256(part + (size_t)bucket * o.cap + pos, lo, hi, spol);
+        stg256(part + (size_t)bucket * o.cap + pos, lo, hi);
     } else {
         const uint32_t k = atomicAdd(o.ovf_count, 1u);
-        if (k < o.ovf_cap) stg256(o.ovf + k, lo, hi, spol);
+        if (k < o.ovf_cap) stg256(o.ovf + k, lo, hi);
     }
 }
 
@@ -126,7 +113,7 @@ __device__ __forceinline__ uint32_t hash_tag(uint64_t h, int bshift)
 }
 
 template <bool SCATTER>
-__device__ __forceinline__ void emit_row(const RowRegs &r, int bshift, uint32_t *counters, Row32 *part, const OptScatter &o, uint64_t spol)
+__device__ __forceinline__ void emit_row(const RowRegs &r, int bshift, uint32_t *counters, Row32 *part, const OptScatter &o)
 {
     if (!r.keep) return;
     const uint64_t h = key_hash(r.a, r.b, r.proto);
@@ -134,7 +121,7 @@ __device__ __forceinline__ void emit_row(const RowRegs &r, int bshift, uint32_t 
     if (SCATTER) {
         RowRegs rt = r;
         rt.proto |= hash_tag(h, bshift) << 8;
-        place_row(rt, bucket, atomicAdd(&counters[bucket], 1u), part, o, spol);
+        place_row(rt, bucket, atomicAdd(&counters[bucket], 1u), part, o);
     } else {
         atomicAdd(&counters[bucket], 1u);
     }
@@ -162,7 +149,6 @@ __global__ void __launch_bounds__(256) partition_kernel(ColPtrs c, uint64_t R, R
 {
     const uint64_t ngroups = (R + 7) / 8;
     const bool need_end = SCATTER || f.end_time != 0;
-    const uint64_t lpol = make_policy(opt.load_pol), spol = make_policy(opt.store_pol);
     for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups;
          g += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t base = g * 8;
@@ -171,16 +157,16 @@ __global__ void __launch_bounds__(256) partition_kernel(ColPtrs c, uint64_t R, R
             uint4 sip0 = z, sip1 = z, dip0 = z, dip1 = z, fs0 = z, fs1 = z, fe0 = z, fe1 = z, sp = z, dp = z;
             uint4 v0 = z, v1 = z, v2 = z, v3 = z;
             uint2 pr = make_uint2(0, 0);
-            if (c.src_ip) { sip0 = ldg_stream128(c.src_ip + base, lpol); sip1 = ldg_stream128(c.src_ip + base + 4, lpol); }
-            if (c.dst_ip) { dip0 = ldg_stream128(c.dst_ip + base, lpol); dip1 = ldg_stream128(c.dst_ip + base + 4, lpol); }
-            if (c.flow_start) { fs0 = ldg_stream128(c.flow_start + base, lpol); fs1 = ldg_stream128(c.flow_start + base + 4, lpol); }
-            if (need_end) { fe0 = ldg_stream128(c.flow_end + base, lpol); fe1 = ldg_stream128(c.flow_end + base + 4, lpol); }
-            if (c.src_port) sp = ldg_stream128(c.src_port + base, lpol);
-            if (c.dst_port) dp = ldg_stream128(c.dst_port + base, lpol);
-            if (c.proto) pr = ldg_stream64(c.proto + base, lpol);
+            if (c.src_ip) { sip0 = ldg_stream128(c.src_ip + base); sip1 = ldg_stream128(c.src_ip + base + 4); }
+            if (c.dst_ip) { dip0 = ldg_stream128(c.dst_ip + base); dip1 = ldg_stream128(c.dst_ip + base + 4); }
+            if (c.flow_start) { fs0 = ldg_stream128(c.flow_start + base); fs1 = ldg_stream128(c.flow_start + base + 4); }
+            if (need_end) { fe0 = ldg_stream128(c.flow_end + base); fe1 = ldg_stream128(c.flow_end + base + 4); }
+            if (c.src_port) sp = ldg_stream128(c.src_port + base);
+            if (c.dst_port) dp = ldg_stream128(c.dst_port + base);
+            if (c.proto) pr = ldg_stream64(c.proto + base);
             if (SCATTER) {
-                v0 = ldg_stream128(c.value + base, lpol); v1 = ldg_stream128(c.value + base + 2, lpol);
-                v2 = ldg_stream128(c.value + base + 4, lpol); v3 = ldg_stream128(c.value + base + 6, lpol);
+                v0 = ldg_stream128(c.value + base); v1 = ldg_stream128(c.value + base + 2);
+                v2 = ldg_stream128(c.value + base + 4); v3 = ldg_stream128(c.value + base + 6);
             }
             const uint32_t sipv[8] = {sip0.x, sip0.y, sip0.z, sip0.w, sip1.x, sip1.y, sip1.z, sip1.w};
             const uint32_t dipv[8] = {dip0.x, dip0.y, dip0.z, dip0.w, dip1.x, dip1.y, dip1.z, dip1.w};
@@ -215,17 +201,17 @@ __global__ void __launch_bounds__(256) partition_kernel(ColPtrs c, uint64_t R, R
                 }
 #pragma unroll
                 for (int i = 0; i < 8; i++)
-                    if (r[i].keep) place_row(r[i], bkt[i], pos[i], part, opt, spol);
+                    if (r[i].keep) place_row(r[i], bkt[i], pos[i], part, opt);
             } else {
 #pragma unroll
-                for (int i = 0; i < 8; i++) emit_row<SCATTER>(r[i], bshift, counters, part, opt, spol);
+                for (int i = 0; i < 8; i++) emit_row<SCATTER>(r[i], bshift, counters, part, opt);
             }
         } else {
             const uint64_t end = base + 8 < R ? base + 8 : R;
             for (uint64_t i = base; i < end; i++) {
                 RowRegs r;
                 load_row_scalar(c, f, i, SCATTER, r);
-                emit_row<SCATTER>(r, bshift, counters, part, opt, spol);
+                emit_row<SCATTER>(r, bshift, counters, part, opt);
             }
         }
     }
@@ -414,8 +400,7 @@ struct GroupSmem {
     static constexpr int HT = 2 * CAP;
     alignas(128) unsigned char x[32 * CAP];   // rows (TMA destination); later ts | tout | vout
     uint32_t ht[HT];                          // claim: low16 = rep row + 1, high16 = count; later (count << 16) | series idx
-    uint16_t soff[CAP];                       // first point of series k inside the bucket (indexed by the dense series index:
-                                              // half the size of a per-slot array, which is what lets five 1024-row CTAs share an SM)
+    uint16_t soff[HT];                        // first point of the slot's series inside the bucket
     alignas(8) unsigned long long mbar;
     uint32_t warp_sums[32];
     uint32_t total;
@@ -599,7 +584,7 @@ __global__ void __launch_bounds__(NT) group_kernel(const SegDesc seg, SeriesEntr
                 const uint32_t so = ex & 0xffffu, k = ex >> 16, cnt = w >> 16, rep = (w & 0xffffu) - 1u;
                 const uint4 kk = x4[2 * rep];
                 const uint32_t pp = x4[2 * rep + 1].w;
-                s.soff[k] = (uint16_t)so;
+                s.soff[base + i] = (uint16_t)so;
                 s.ht[base + i] = (cnt << 16) | k;
                 // series entry, in place over the (already staged) bucket rows
                 uint4 *e4 = reinterpret_cast<uint4 *>(ent + k);
@@ -643,8 +628,8 @@ __global__ void __launch_bounds__(NT) group_kernel(const SegDesc seg, SeriesEntr
         myB[j] = 0;
         if (r < n) {
             const uint32_t slot = mySP[j] & 0xffffu;
-            const uint32_t w = s.ht[slot];
-            const uint32_t cnt = w >> 16, k = w & 0xffffu, so = s.soff[k];
+            const uint32_t w = s.ht[slot], so = s.soff[slot];
+            const uint32_t cnt = w >> 16, k = w & 0xffffu;
             const uint32_t lo = tmin[k], range = tmax[k] - lo;
             uint32_t bin = 0;
             if (range) {
@@ -695,7 +680,7 @@ __global__ void __launch_bounds__(NT) group_kernel(const SegDesc seg, SeriesEntr
             tout[pos] = t;
             vout[pos] = myV[j];
             if (VRANK) pslot[pos] = (uint16_t)slot;
-            mySP[j] = pos | ((pos > s.soff[s.ht[slot] & 0xffffu] ? 1u : 0u) << 31);
+            mySP[j] = pos | ((pos > s.soff[slot] ? 1u : 0u) << 31);
         }
     }
     __syncthreads();
@@ -717,7 +702,7 @@ __global__ void __launch_bounds__(NT) group_kernel(const SegDesc seg, SeriesEntr
             const uint32_t w = s.ht[sl];
             const uint32_t cnt = w >> 16;
             if (cnt < 2) continue;
-            const uint32_t so = s.soff[w & 0xffffu];
+            const uint32_t so = s.soff[sl];
             uint32_t wr = 0;
             for (uint32_t q = 1; q < cnt; q++) {
                 if (tout[so + q] == tout[so + wr]) {
@@ -746,8 +731,7 @@ __global__ void __launch_bounds__(NT) group_kernel(const SegDesc seg, SeriesEntr
         __syncthreads();
         for (uint32_t p = tid; p < n; p += NT) {
             const uint32_t slot = pslot[p];
-            const uint32_t hw = s.ht[slot];
-            const uint32_t so = s.soff[hw & 0xffffu], cnt = hw >> 16, me = p - so;
+            const uint32_t so = s.soff[slot], cnt = s.ht[slot] >> 16, me = p - so;
             if (me >= cnt) continue;                    // hole left by the duplicate reduce
             const unsigned long long v = vout[p];
             uint32_t rank = (v == ~0ull) ? me : count_lt_u64(vout, so, so + me, v + 1ull);
@@ -905,13 +889,11 @@ struct DetectSmem {
     double qcalc[kDetectQueue];
     uint32_t qmeta[kDetectQueue];                     // bit 31: flag, bits 30..16: owning thread, low 16: unused
     uint32_t qpos[kDetectQueue];                      // index of the point in csr_v / csr_t
-    uint32_t qt[kDetectQueue];                        // flowEndSeconds of the queued rows (filled before the column writes)
     unsigned long long ent_a[kDetectThreads], ent_b[kDetectThreads];
     double ent_sd[kDetectThreads];
     uint32_t ent_proto[kDetectThreads];
     alignas(8) unsigned long long mbar;
-    uint32_t span_lo, span_hi, base, b0;
-    uint32_t wq[kDetectThreads / 32], wpre[kDetectThreads / 32];   // rows queued per warp, exclusive prefix
+    uint32_t span_lo, span_hi, qcount, base, b0;
     uint32_t win[kBucketWindow + 1], woff[kBucketWindow + 1];
 };
 
@@ -927,6 +909,7 @@ __global__ void __launch_bounds__(NT) detect_ewma_kernel(const SeriesEntry *__re
     if (threadIdx.x == 0) {
         sm.span_lo = 0xffffffffu;
         sm.span_hi = 0u;
+        sm.qcount = 0u;
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&sm.mbar)), "r"(1));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -963,66 +946,39 @@ __global__ void __launch_bounds__(NT) detect_ewma_kernel(const SeriesEntry *__re
                          : "=r"(done) : "r"(smem_u32(&sm.mbar)), "r"(0) : "memory");
         }
     }
+    const uint64_t *v = staged ? reinterpret_cast<const uint64_t *>(sm.stage) + (e.off - lo_a) : csr_v + e.off;
     bool has_sd = false;
     double sd = 0.0;
     if (e.n) {
-        // two call sites so that each is compiled for its address space (LDS from the stage, LDG otherwise)
-        sd = staged ? series_stddev(reinterpret_cast<const uint64_t *>(sm.stage) + (e.off - lo_a), e.n, has_sd)
-                    : series_stddev(csr_v + e.off, e.n, has_sd);
+        sd = series_stddev(v, e.n, has_sd);
         sm.ent_a[threadIdx.x] = e.a; sm.ent_b[threadIdx.x] = e.b; sm.ent_proto[threadIdx.x] = e.proto;
         sm.ent_sd[threadIdx.x] = sd;
-    }
-    // ---- EWMA + flag, warp-synchronous: every lane walks its own series, all lanes of a warp step together, so the
-    // queue slot of a flagged point comes from one ballot and a warp-uniform register counter (no shared-memory atomic on
-    // the per-step path).  Each warp owns a fixed region of the queue; what does not fit is emitted directly.
-    constexpr uint32_t kWarps = NT / 32, kWarpQueue = kDetectQueue / kWarps;
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint32_t wbase = warp * kWarpQueue;
-    const uint32_t n_act = (e.n && (has_sd || emit_all)) ? e.n : 0u;
-    const uint32_t n_max = __reduce_max_sync(0xffffffffu, n_act);
-    uint32_t wcount = 0;
-    double prev = 0.0;
-    for (uint32_t q = 0; q < n_max; q++) {
-        const bool act = q < n_act;
-        const unsigned long long raw = !act ? 0ull : (staged ? sm.stage[e.off - lo_a + q] : csr_v[e.off + q]);
-        const double x = __ull2double_rn(raw);
-        prev = __dadd_rn(__dmul_rn(0.5, prev), __dmul_rn(0.5, x));
-        const bool flag = act && has_sd && (fabs(__dsub_rn(x, prev)) > sd);
-        const bool push = act && (flag || emit_all);
-        const uint32_t mask = __ballot_sync(0xffffffffu, push);
-        if (mask == 0u) continue;
-        const uint32_t slot = wcount + (uint32_t)__popc(mask & ((1u << lane) - 1u));
-        wcount += (uint32_t)__popc(mask);
-        if (push) {
-            if (slot < kWarpQueue) {
-                sm.qcalc[wbase + slot] = prev;
-                sm.qpos[wbase + slot] = e.off + q;
-                sm.qmeta[wbase + slot] = (flag ? 0x80000000u : 0u) | (threadIdx.x << 16);
-            } else {                                            // region full: direct emission
-                const uint32_t idx = atomicAdd(&stats[ST_OUTCOUNT], 1u);
-                if (idx < out_cap) write_out(out, idx, e, csr_t[e.off + q], sd, prev, x, flag);
-            }
+        if (has_sd || emit_all) {
+            double prev = 0.0;
+            for_each_value(v, e.n, [&](uint64_t raw, uint32_t q) {
+                const double x = __ull2double_rn(raw);
+                prev = __dadd_rn(__dmul_rn(0.5, prev), __dmul_rn(0.5, x));
+                const bool flag = has_sd && (fabs(__dsub_rn(x, prev)) > sd);
+                if (flag || emit_all) {
+                    const uint32_t slot = atomicAdd(&sm.qcount, 1u);
+                    if (slot < (uint32_t)kDetectQueue) {
+                        sm.qcalc[slot] = prev;
+                        sm.qpos[slot] = e.off + q;
+                        sm.qmeta[slot] = (flag ? 0x80000000u : 0u) | (threadIdx.x << 16);
+                    } else {                                        // queue full: direct emission
+                        const uint32_t idx = atomicAdd(&stats[ST_OUTCOUNT], 1u);
+                        if (idx < out_cap) write_out(out, idx, e, csr_t[e.off + q], sd, prev, x, flag);
+                    }
+                }
+            });
         }
     }
-    if (lane == 0) sm.wq[warp] = min(wcount, kWarpQueue);
     __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t nq = 0;
-        for (uint32_t w = 0; w < kWarps; w++) { sm.wpre[w] = nq; nq += sm.wq[w]; }
-        sm.base = nq ? atomicAdd(&stats[ST_OUTCOUNT], nq) : 0u;
-    }
+    const uint32_t nq = min(sm.qcount, (uint32_t)kDetectQueue);
+    if (threadIdx.x == 0) sm.base = nq ? atomicAdd(&stats[ST_OUTCOUNT], nq) : 0u;
     __syncthreads();
-    // ---- cooperative emission.  First the flow_end of every queued row (independent global loads, nothing between
-    // them that could alias), then the eleven coalesced column writes.
-#pragma unroll 4
-    for (uint32_t j = threadIdx.x; j < kWarps * kWarpQueue; j += NT) {
-        const uint32_t w = j / kWarpQueue, k = j - w * kWarpQueue;
-        if (k < sm.wq[w]) sm.qt[j] = csr_t[sm.qpos[j]];
-    }
-    for (uint32_t j = threadIdx.x; j < kWarps * kWarpQueue; j += NT) {
-        const uint32_t w = j / kWarpQueue, k = j - w * kWarpQueue;
-        if (k >= sm.wq[w]) continue;
-        const uint32_t idx = sm.base + sm.wpre[w] + k;
+    for (uint32_t j = threadIdx.x; j < nq; j += NT) {
+        const uint32_t idx = sm.base + j;
         if (idx >= out_cap) continue;
         const uint32_t meta = sm.qmeta[j], pos = sm.qpos[j], owner = (meta >> 16) & 0x7fffu;
         const uint64_t ka = sm.ent_a[owner], kb = sm.ent_b[owner];
@@ -1032,7 +988,7 @@ __global__ void __launch_bounds__(NT) detect_ewma_kernel(const SeriesEntry *__re
         out.src_port[idx] = (uint16_t)(kb >> 16);
         out.dst_port[idx] = (uint16_t)kb;
         out.proto[idx] = (uint8_t)sm.ent_proto[owner];
-        out.flow_end[idx] = sm.qt[j];
+        out.flow_end[idx] = csr_t[pos];
         out.stddev[idx] = sm.ent_sd[owner];
         out.algo_calc[idx] = sm.qcalc[j];
         out.throughput[idx] = __ull2double_rn(staged ? sm.stage[pos - lo_a] : csr_v[pos]);
@@ -1042,11 +998,13 @@ __global__ void __launch_bounds__(NT) detect_ewma_kernel(const SeriesEntry *__re
 
 // ----------------------------------------------------------------------------------------
 // K4, direct variant: no shared-memory stage.  A thread streams its own series straight out of csr_v, one full
-// 32-byte sector (four values, two 128-bit loads through the read-only path) per step with the next sector already
-// in flight, so nothing is fetched twice and the kernel runs at register-limited occupancy (5 CTAs of 128 threads
-// per SM instead of two of 96): the FP64 chains of ~600 threads per SM hide the memory latency that the staged
-// variant pays CTA by CTA.  Sectors are addressed from the sector-aligned start of the series (csr_v is padded by
-// one sector), elements outside [0, n) are masked.  The EWMA pass is warp-synchronous (queue slots from one ballot).
+// 32-byte sector (four values, ONE 256-bit load through the read-only path) per step with the next sector already
+// in flight, so no sector is fetched twice and the kernel runs at register-limited occupancy (5 CTAs of 128 threads
+// per SM instead of two of 96).  The staged variant is latency bound -- 6 warps per SM on dependent FP64 chains issue
+// ~0.75 instructions per clock and SM (profiles/r01_source_lines_detect.txt) -- and this one attacks exactly that with
+// more warps.  Sectors are addressed from the sector-aligned start of the series (csr_v is padded by one sector),
+// elements outside [0, n) are masked.  Flagged points are queued in shared memory (one warp-aggregated atomic per
+// flagged point) and written out cooperatively, every result column coalesced.
 // ----------------------------------------------------------------------------------------
 constexpr int kDirectThreads = 128;
 constexpr int kDirectQueue = 2048;                    // queued result rows per CTA (16 per series; the bench table has ~9)
@@ -1058,15 +1016,16 @@ struct DirectSmem {
     unsigned long long ent_a[kDirectThreads], ent_b[kDirectThreads];
     double ent_sd[kDirectThreads];
     uint32_t ent_proto[kDirectThreads];
-    uint32_t base, b0;
-    uint32_t wq[kDirectThreads / 32], wpre[kDirectThreads / 32];
+    uint32_t qcount, base, b0;
     uint32_t win[kBucketWindow + 1], woff[kBucketWindow + 1];
 };
 
-__device__ __forceinline__ ulonglong2 ldg_nc_u64x2(const uint64_t *p)
+struct Sector4 { unsigned long long v[4]; };
+__device__ __forceinline__ Sector4 ldg_sector(const uint64_t *p)      // p is 32-byte aligned
 {
-    ulonglong2 r;
-    asm volatile("ld.global.nc.v2.u64 {%0,%1}, [%2];" : "=l"(r.x), "=l"(r.y) : "l"(p));
+    Sector4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];"
+                 : "=l"(r.v[0]), "=l"(r.v[1]), "=l"(r.v[2]), "=l"(r.v[3]) : "l"(p));
     return r;
 }
 __device__ __forceinline__ uint32_t ldg_nc_u32(const uint32_t *p)
@@ -1090,9 +1049,10 @@ __global__ void __launch_bounds__(NT, 5) detect_ewma_direct_kernel(const SeriesE
 {
     __shared__ DirectSmem sm;
     const uint32_t i = blockIdx.x * NT + threadIdx.x;
+    if (threadIdx.x == 0) sm.qcount = 0u;
     SeriesEntry e;
     e.n = 0; e.off = 0; e.a = 0; e.b = 0; e.proto = 0;
-    const uint32_t bkt = find_bucket_cta(sbase, offsets, B, i < S ? i : S - 1, blockIdx.x * NT, sm.win, sm.woff, &sm.b0);
+    const uint32_t bkt = find_bucket_cta(sbase, offsets, B, i < S ? i : S - 1, blockIdx.x * NT, sm.win, sm.woff, &sm.b0);   // syncs
     if (i < S) {
         const uint32_t wk = bkt - sm.b0;
         const bool inwin = wk < (uint32_t)kBucketWindow;
@@ -1106,17 +1066,16 @@ __global__ void __launch_bounds__(NT, 5) detect_ewma_direct_kernel(const SeriesE
     const uint64_t *vs = csr_v + (e.off & ~3u);                   // sector-aligned start of the series
     const uint32_t ng = n ? ((uint32_t)mis + n + 3u) >> 2 : 0u;   // sectors the series touches
 
-    // ---- pass 1: stddev_samp (Welford in time order; see series_stddev for the exact-division argument) -------------
     bool has_sd = false;
     double sd = 0.0;
     if (n) {
+        // ---- pass 1: stddev_samp (Welford in time order; see series_stddev for the exact-division argument) ---------
         double cnt = 0.0, avg = 0.0, m2 = 0.0;
-        ulonglong2 a = ldg_nc_u64x2(vs), b = ldg_nc_u64x2(vs + 2);
+        Sector4 cur = ldg_sector(vs);
         for (uint32_t g = 0; g < ng; g++) {
-            ulonglong2 na = a, nb = b;
-            if (g + 1 < ng) { na = ldg_nc_u64x2(vs + 4 * (g + 1)); nb = ldg_nc_u64x2(vs + 4 * (g + 1) + 2); }
+            Sector4 nxt = cur;
+            if (g + 1 < ng) nxt = ldg_sector(vs + 4 * (g + 1));
             const int i0 = (int)(4 * g) - mis;                    // element index of the sector's first value
-            const unsigned long long raw[4] = {a.x, a.y, b.x, b.y};
             double rc[4];
 #pragma unroll
             for (int j = 0; j < 4; j++) rc[j] = g_rcp[min((uint32_t)max(i0 + j + 1, 0), kRcpTable)];
@@ -1124,7 +1083,7 @@ __global__ void __launch_bounds__(NT, 5) detect_ewma_direct_kernel(const SeriesE
             for (int j = 0; j < 4; j++) {
                 const int idx = i0 + j;
                 if (idx >= 0 && idx < (int)n) {
-                    const double x = __ull2double_rn(raw[j]);
+                    const double x = __ull2double_rn(cur.v[j]);
                     cnt = __dadd_rn(cnt, 1.0);
                     const double d = __dsub_rn(x, avg);
                     double dn;
@@ -1138,87 +1097,68 @@ __global__ void __launch_bounds__(NT, 5) detect_ewma_direct_kernel(const SeriesE
                     m2 = __dadd_rn(m2, __dmul_rn(d, __dsub_rn(d, dn)));
                 }
             }
-            a = na; b = nb;
+            cur = nxt;
         }
         has_sd = n >= 2;
         sd = has_sd ? __dsqrt_rn(__ddiv_rn(m2, __dsub_rn(cnt, 1.0))) : __longlong_as_double(0x7ff8000000000000LL);
         sm.ent_a[threadIdx.x] = e.a; sm.ent_b[threadIdx.x] = e.b; sm.ent_proto[threadIdx.x] = e.proto;
         sm.ent_sd[threadIdx.x] = sd;
-    }
-
-    // ---- pass 2: EWMA + flag, warp-synchronous --------------------------------------------------------------------
-    constexpr uint32_t kWarps = NT / 32, kWarpQueue = kDirectQueue / kWarps;
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint32_t wbase = warp * kWarpQueue;
-    const uint32_t n_act = (n && (has_sd || emit_all)) ? n : 0u;
-    const uint32_t ng_act = n_act ? ng : 0u;
-    const uint32_t ng_max = __reduce_max_sync(0xffffffffu, ng_act);
-    uint32_t wcount = 0;
-    double prev = 0.0;
-    ulonglong2 a = make_ulonglong2(0ull, 0ull), b = a;
-    if (ng_act) { a = ldg_nc_u64x2(vs); b = ldg_nc_u64x2(vs + 2); }
-    for (uint32_t g = 0; g < ng_max; g++) {
-        ulonglong2 na = a, nb = b;
-        if (g + 1 < ng_act) { na = ldg_nc_u64x2(vs + 4 * (g + 1)); nb = ldg_nc_u64x2(vs + 4 * (g + 1) + 2); }
-        const int i0 = (int)(4 * g) - mis;
-        const unsigned long long raw[4] = {a.x, a.y, b.x, b.y};
+        // ---- pass 2: EWMA + flag; flagged points go to the CTA's queue ---------------------------------------------
+        if (has_sd || emit_all) {
+            double prev = 0.0;
+            cur = ldg_sector(vs);
+            for (uint32_t g = 0; g < ng; g++) {
+                Sector4 nxt = cur;
+                if (g + 1 < ng) nxt = ldg_sector(vs + 4 * (g + 1));
+                const int i0 = (int)(4 * g) - mis;
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const int idx = i0 + j;
-            const bool act = g < ng_act && idx >= 0 && idx < (int)n_act;
-            const double x = __ull2double_rn(raw[j]);
-            if (act) prev = __dadd_rn(__dmul_rn(0.5, prev), __dmul_rn(0.5, x));
-            const bool flag = act && has_sd && (fabs(__dsub_rn(x, prev)) > sd);
-            const bool push = act && (flag || emit_all);
-            const uint32_t mask = __ballot_sync(0xffffffffu, push);
-            if (mask == 0u) continue;
-            const uint32_t slot = wcount + (uint32_t)__popc(mask & ((1u << lane) - 1u));
-            wcount += (uint32_t)__popc(mask);
-            if (push) {
-                if (slot < kWarpQueue) {
-                    sm.qcalc[wbase + slot] = prev;
-                    sm.qpos[wbase + slot] = e.off + (uint32_t)idx;
-                    sm.qmeta[wbase + slot] = (flag ? 0x80000000u : 0u) | (threadIdx.x << 16);
-                } else {                                            // region full: direct emission
-                    const uint32_t o = atomicAdd(&stats[ST_OUTCOUNT], 1u);
-                    if (o < out_cap) write_out(out, o, e, csr_t[e.off + (uint32_t)idx], sd, prev, x, flag);
+                for (int j = 0; j < 4; j++) {
+                    const int idx = i0 + j;
+                    if (idx >= 0 && idx < (int)n) {
+                        const double x = __ull2double_rn(cur.v[j]);
+                        prev = __dadd_rn(__dmul_rn(0.5, prev), __dmul_rn(0.5, x));
+                        const bool flag = has_sd && (fabs(__dsub_rn(x, prev)) > sd);
+                        if (flag || emit_all) {
+                            const uint32_t slot = atomicAdd(&sm.qcount, 1u);
+                            if (slot < (uint32_t)kDirectQueue) {
+                                sm.qcalc[slot] = prev;
+                                sm.qpos[slot] = e.off + (uint32_t)idx;
+                                sm.qmeta[slot] = (flag ? 0x80000000u : 0u) | (threadIdx.x << 16);
+                            } else {                                    // queue full: direct emission
+                                const uint32_t o = atomicAdd(&stats[ST_OUTCOUNT], 1u);
+                                if (o < out_cap) write_out(out, o, e, csr_t[e.off + (uint32_t)idx], sd, prev, x, flag);
+                            }
+                        }
+                    }
                 }
+                cur = nxt;
             }
         }
-        a = na; b = nb;
     }
-    if (lane == 0) sm.wq[warp] = min(wcount, kWarpQueue);
     __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t nq = 0;
-        for (uint32_t w = 0; w < kWarps; w++) { sm.wpre[w] = nq; nq += sm.wq[w]; }
-        sm.base = nq ? atomicAdd(&stats[ST_OUTCOUNT], nq) : 0u;
-    }
+    const uint32_t nq = min(sm.qcount, (uint32_t)kDirectQueue);
+    if (threadIdx.x == 0) sm.base = nq ? atomicAdd(&stats[ST_OUTCOUNT], nq) : 0u;
     __syncthreads();
     // ---- cooperative emission: one result row per thread and step, every column written coalesced; flowEndSeconds and
     // throughput come through the read-only path, so the loads of a step are all in flight before its first store
-    for (uint32_t w = 0; w < kWarps; w++) {
-        const uint32_t cnt_w = sm.wq[w], out0 = sm.base + sm.wpre[w];
-        for (uint32_t k = threadIdx.x; k < cnt_w; k += NT) {
-            const uint32_t idx = out0 + k;
-            if (idx >= out_cap) continue;
-            const uint32_t j = w * kWarpQueue + k;
-            const uint32_t meta = sm.qmeta[j], pos = sm.qpos[j], owner = (meta >> 16) & 0x7fffu;
-            const uint32_t t = ldg_nc_u32(csr_t + pos);
-            const unsigned long long xv = ldg_nc_u64(csr_v + pos);
-            const uint64_t ka = sm.ent_a[owner], kb = sm.ent_b[owner];
-            out.src_ip[idx] = (uint32_t)(ka >> 32);
-            out.dst_ip[idx] = (uint32_t)ka;
-            out.flow_start[idx] = (uint32_t)(kb >> 32);
-            out.src_port[idx] = (uint16_t)(kb >> 16);
-            out.dst_port[idx] = (uint16_t)kb;
-            out.proto[idx] = (uint8_t)sm.ent_proto[owner];
-            out.flow_end[idx] = t;
-            out.stddev[idx] = sm.ent_sd[owner];
-            out.algo_calc[idx] = sm.qcalc[j];
-            out.throughput[idx] = __ull2double_rn(xv);
-            out.anomaly[idx] = (meta >> 31) ? 1 : 0;
-        }
+    for (uint32_t j = threadIdx.x; j < nq; j += NT) {
+        const uint32_t idx = sm.base + j;
+        if (idx >= out_cap) continue;
+        const uint32_t meta = sm.qmeta[j], pos = sm.qpos[j], owner = (meta >> 16) & 0x7fffu;
+        const uint32_t t = ldg_nc_u32(csr_t + pos);
+        const unsigned long long xv = ldg_nc_u64(csr_v + pos);
+        const uint64_t ka = sm.ent_a[owner], kb = sm.ent_b[owner];
+        out.src_ip[idx] = (uint32_t)(ka >> 32);
+        out.dst_ip[idx] = (uint32_t)ka;
+        out.flow_start[idx] = (uint32_t)(kb >> 32);
+        out.src_port[idx] = (uint16_t)(kb >> 16);
+        out.dst_port[idx] = (uint16_t)kb;
+        out.proto[idx] = (uint8_t)sm.ent_proto[owner];
+        out.flow_end[idx] = t;
+        out.stddev[idx] = sm.ent_sd[owner];
+        out.algo_calc[idx] = sm.qcalc[j];
+        out.throughput[idx] = __ull2double_rn(xv);
+        out.anomaly[idx] = (meta >> 31) ? 1 : 0;
     }
 }
 
@@ -1367,23 +1307,11 @@ static uint32_t partition_grid(uint64_t R)
     return (uint32_t)(want < cap ? (want ? want : 1) : cap);
 }
 
-// TAD_SCATTER_LOADPOL / TAD_SCATTER_STOREPOL: 0 = evict_normal (default), 1 = evict_first, 2 = evict_last
-static int partition_policy(int which)
-{
-    static int pol[2] = {-1, -1};
-    if (pol[0] < 0) {
-        const char *a = getenv("TAD_SCATTER_LOADPOL"), *b = getenv("TAD_SCATTER_STOREPOL");
-        pol[0] = a ? atoi(a) : 0;
-        pol[1] = b ? atoi(b) : 0;
-    }
-    return pol[which];
-}
-
 cudaError_t launch_hist(cudaStream_t st, const ColPtrs &c, uint64_t R, const RowFilter &f, int logB, uint32_t *hist)
 {
     if (R == 0) return cudaSuccess;
     const int bshift = 64 - logB;
-    const OptScatter none{0, 0, nullptr, nullptr, partition_policy(0), 0};
+    const OptScatter none{0, 0, nullptr, nullptr};
     if (cols_aligned16(c))
         partition_kernel<false, true><<<partition_grid(R), 256, 0, st>>>(c, R, f, bshift, hist, nullptr, none);
     else
@@ -1396,7 +1324,7 @@ cudaError_t launch_scatter(cudaStream_t st, const ColPtrs &c, uint64_t R, const 
 {
     if (R == 0) return cudaSuccess;
     const int bshift = 64 - logB;
-    const OptScatter opt{slot_cap, ovf_cap, ovf, ovf_count, partition_policy(0), partition_policy(1)};
+    const OptScatter opt{slot_cap, ovf_cap, ovf, ovf_count};
     if (cols_aligned16(c))
         partition_kernel<true, true><<<partition_grid(R), 256, 0, st>>>(c, R, f, bshift, cursor, part, opt);
     else
