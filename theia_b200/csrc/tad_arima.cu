@@ -153,37 +153,59 @@ __host__ __device__ __forceinline__ void arima_transform(const double u[3], doub
     s2 = u[2] * u[2];
 }
 
+// One filter: the state the recursion carries (a2 = p02 = 0, p12 = q12, p22 = q22 after every prediction step, so they are
+// constants of the parameters) and one time step.  arima_loglike runs one of these; arima_fg runs FOUR side by side in one
+// loop -- the objective at u and at its three forward-difference neighbours -- so that a lane has four independent FP64
+// dependency chains in flight instead of one (the arithmetic of every chain is exactly that of the single filter).
+struct Kalman {
+    double phi, q11, q12, q22;
+    double a0, a1, a2, p00, p01, p02, p11, p12, p22, ll;
+    bool dead;                       // F <= 0 or not finite at some step: the likelihood is -1e300 (statsmodels raises)
+};
+
+__host__ __device__ __forceinline__ void kalman_init(Kalman &k, double phi, double theta, double s2)
+{
+    k.phi = phi;
+    k.a0 = 0.0; k.a1 = 0.0; k.a2 = 0.0;
+    k.p00 = kDiffuse; k.p01 = 0.0; k.p02 = 0.0;
+    k.p11 = s2 * (1.0 + 2.0 * phi * theta + theta * theta) / (1.0 - phi * phi);
+    k.p12 = s2 * theta; k.p22 = s2 * theta * theta;
+    k.q11 = s2; k.q12 = s2 * theta; k.q22 = s2 * theta * theta;
+    k.ll = 0.0;
+    k.dead = false;
+}
+
+__host__ __device__ __forceinline__ void kalman_step(Kalman &k, double yt, bool count)
+{
+    const double v = yt - (k.a0 + k.a1);
+    const double F = k.p00 + 2.0 * k.p01 + k.p11;
+    if (!(F > 0.0) || !isfinite(F)) { k.dead = true; return; }
+    if (count) k.ll += -0.5 * (kLog2Pi + log(F) + v * v / F);
+    const double z0 = k.p00 + k.p01, z1 = k.p01 + k.p11, z2 = k.p02 + k.p12;
+    const double g = v / F;
+    const double f0 = k.a0 + z0 * g, f1 = k.a1 + z1 * g, f2 = k.a2 + z2 * g;
+    const double c00 = k.p00 - z0 * z0 / F, c01 = k.p01 - z0 * z1 / F, c02 = k.p02 - z0 * z2 / F;
+    const double c11 = k.p11 - z1 * z1 / F, c12 = k.p12 - z1 * z2 / F, c22 = k.p22 - z2 * z2 / F;
+    k.a0 = f0 + f1; k.a1 = k.phi * f1 + f2; k.a2 = 0.0;
+    k.p00 = c00 + 2.0 * c01 + c11;
+    k.p01 = k.phi * (c01 + c11) + c02 + c12;
+    k.p02 = 0.0;
+    k.p11 = k.phi * k.phi * c11 + 2.0 * k.phi * c12 + c22 + k.q11;
+    k.p12 = k.q12;
+    k.p22 = k.q22;
+}
+
 __host__ __device__ double arima_loglike(const ArimaObj &o, double phi, double theta, double s2, double *forecast)
 {
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-    double p00 = kDiffuse, p01 = 0.0, p02 = 0.0;
-    double p11 = s2 * (1.0 + 2.0 * phi * theta + theta * theta) / (1.0 - phi * phi);
-    double p12 = s2 * theta, p22 = s2 * theta * theta;
-    const double q11 = s2, q12 = s2 * theta, q22 = s2 * theta * theta;
-    double ll = 0.0;
-    for (uint32_t t = 0; t < o.n; t++) {
-        const double v = o.y[t] - (a0 + a1);
-        const double F = p00 + 2.0 * p01 + p11;
-        if (!(F > 0.0) || !isfinite(F)) {
-            if (forecast) *forecast = 0.0;
-            return -1e300;
-        }
-        if (t >= 1) ll += -0.5 * (kLog2Pi + log(F) + v * v / F);
-        const double z0 = p00 + p01, z1 = p01 + p11, z2 = p02 + p12;
-        const double g = v / F;
-        const double f0 = a0 + z0 * g, f1 = a1 + z1 * g, f2 = a2 + z2 * g;
-        const double c00 = p00 - z0 * z0 / F, c01 = p01 - z0 * z1 / F, c02 = p02 - z0 * z2 / F;
-        const double c11 = p11 - z1 * z1 / F, c12 = p12 - z1 * z2 / F, c22 = p22 - z2 * z2 / F;
-        a0 = f0 + f1; a1 = phi * f1 + f2; a2 = 0.0;
-        p00 = c00 + 2.0 * c01 + c11;
-        p01 = phi * (c01 + c11) + c02 + c12;
-        p02 = 0.0;
-        p11 = phi * phi * c11 + 2.0 * phi * c12 + c22 + q11;
-        p12 = q12;
-        p22 = q22;
+    Kalman k;
+    kalman_init(k, phi, theta, s2);
+    for (uint32_t t = 0; t < o.n && !k.dead; t++) kalman_step(k, o.y[t], t >= 1);
+    if (k.dead) {
+        if (forecast) *forecast = 0.0;
+        return -1e300;
     }
-    if (forecast) *forecast = a0 + a1;
-    return ll;
+    if (forecast) *forecast = k.a0 + k.a1;
+    return k.ll;
 }
 
 __host__ __device__ __forceinline__ double arima_objective(const ArimaObj &o, const double u[3])
@@ -193,15 +215,28 @@ __host__ __device__ __forceinline__ double arima_objective(const ArimaObj &o, co
     return -arima_loglike(o, phi, theta, s2, nullptr) / (double)o.n;
 }
 
+// f and the forward-difference gradient (step 1e-8, as SciPy's approx_fprime drives L-BFGS-B): four filters in one loop
 __host__ __device__ void arima_fg(const ArimaObj &o, double u[3], double &f, double g[3])
 {
-    f = arima_objective(o, u);
-    for (int i = 0; i < 3; i++) {
-        const double save = u[i];
-        u[i] = save + 1e-8;
-        g[i] = (arima_objective(o, u) - f) / 1e-8;
-        u[i] = save;
+    Kalman k[4];
+    for (int c = 0; c < 4; c++) {
+        double uc[3] = {u[0], u[1], u[2]};
+        if (c > 0) uc[c - 1] = u[c - 1] + 1e-8;
+        double phi, theta, s2;
+        arima_transform(uc, phi, theta, s2);
+        kalman_init(k[c], phi, theta, s2);
     }
+    for (uint32_t t = 0; t < o.n; t++) {
+        const double yt = o.y[t];
+        const bool count = t >= 1;
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+            if (!k[c].dead) kalman_step(k[c], yt, count);
+    }
+    double fv[4];
+    for (int c = 0; c < 4; c++) fv[c] = -(k[c].dead ? -1e300 : k[c].ll) / (double)o.n;
+    f = fv[0];
+    for (int c = 0; c < 3; c++) g[c] = (fv[c + 1] - f) / 1e-8;
 }
 
 // Least-squares solution of a two-regressor problem from its normal equations, following numpy.linalg.pinv:
