@@ -42,3 +42,37 @@ def test_reference_arm_runs_on_cpu():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
                           "--ref-series", "100"], capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_sample_mask_is_the_same_subset_for_torch_and_numpy_columns():
+    """bench.py's parity key selects connections by a hash of (sourceIP, destinationIP): the device-side selection of
+    input rows (torch, signed bit patterns) and the host-side selection of result rows (numpy) must agree."""
+    import numpy as np
+    import torch
+    sys.path.insert(0, ROOT)
+    import bench
+    rng = np.random.default_rng(0)
+    a = rng.integers(0, 1 << 32, 20000, dtype=np.uint64).astype(np.uint32)
+    b = rng.integers(0, 1 << 32, 20000, dtype=np.uint64).astype(np.uint32)
+    ta = torch.from_numpy(a.view(np.int32).copy())
+    tb = torch.from_numpy(b.view(np.int32).copy())
+    for frac in (0.001, 0.05, 1.0):
+        m_np = bench.sample_mask(a, b, frac)
+        m_t = bench.sample_mask(ta, tb, frac).numpy()
+        assert np.array_equal(m_np, m_t)
+        assert abs(m_np.mean() - frac) < 0.01 + 0.2 * frac
+
+
+def test_sharded_generator_is_balanced_and_spreads_every_connection():
+    import numpy as np
+    from theia_b200 import synth
+    for world in (2, 4, 8):
+        parts = [synth.torch_cols_to_numpy(synth.make_flows_torch_sharded(25, 100, 3, "cpu", r, world)) for r in range(world)]
+        assert len({len(p["value"]) for p in parts}) == 1            # every rank holds the same number of rows
+        t = {k: np.concatenate([p[k] for p in parts]) for k in parts[0]}
+        key = t["src_ip"].astype(np.uint64) << np.uint64(32) | t["flow_start"].astype(np.uint64)
+        _, counts = np.unique(key, return_counts=True)
+        assert len(counts) == 25 * world and (counts == 100).all()
+        for p in parts:                                                # a connection's points live on every rank
+            k = p["src_ip"].astype(np.uint64) << np.uint64(32) | p["flow_start"].astype(np.uint64)
+            assert len(np.unique(k)) == 25 * world

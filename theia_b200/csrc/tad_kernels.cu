@@ -217,6 +217,65 @@ __global__ void __launch_bounds__(256) partition_kernel(ColPtrs c, uint64_t R, R
     }
 }
 
+// Scatter, four rows per thread (EXPERIMENT, TAD_SCATTER_RPT=4).  The eight-row kernel above needs 122 registers: two CTAs
+// (16 warps) per SM, and ncu shows it latency bound with head-room everywhere -- 30 of its 35 resident warp-cycles per issued
+// instruction are long-scoreboard waits, L2 at 40 %, DRAM at 27 %, LSU at 31 % (profiles/r01_ncu_full_final.txt).  Half the rows
+// per thread halve the live state: <= 64 registers, four CTAs (32 warps) per SM, twice the loads / atomics / stores in flight.
+__global__ void __launch_bounds__(256, 4) scatter4_kernel(ColPtrs c, uint64_t R, RowFilter f, int bshift,
+                                                          uint32_t *__restrict__ counters, Row32 *__restrict__ part,
+                                                          const OptScatter opt)
+{
+    const uint64_t ngroups = (R + 3) / 4;
+    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t base = g * 4;
+        if (base + 4 <= R) {
+            uint4 z = make_uint4(0, 0, 0, 0);
+            uint4 sip = z, dip = z, fs = z, fe, v0, v1;
+            uint2 sp = make_uint2(0, 0), dp = make_uint2(0, 0);
+            uint32_t pr = 0;
+            if (c.src_ip) sip = ldg_stream128(c.src_ip + base);
+            if (c.dst_ip) dip = ldg_stream128(c.dst_ip + base);
+            if (c.flow_start) fs = ldg_stream128(c.flow_start + base);
+            fe = ldg_stream128(c.flow_end + base);
+            if (c.src_port) sp = ldg_stream64(c.src_port + base);
+            if (c.dst_port) dp = ldg_stream64(c.dst_port + base);
+            if (c.proto) asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(pr) : "l"(c.proto + base));
+            v0 = ldg_stream128(c.value + base);
+            v1 = ldg_stream128(c.value + base + 2);
+            const uint32_t sipv[4] = {sip.x, sip.y, sip.z, sip.w}, dipv[4] = {dip.x, dip.y, dip.z, dip.w};
+            const uint32_t fsv[4] = {fs.x, fs.y, fs.z, fs.w}, fev[4] = {fe.x, fe.y, fe.z, fe.w};
+            const uint32_t spw[2] = {sp.x, sp.y}, dpw[2] = {dp.x, dp.y};
+            const uint32_t vlo[4] = {v0.x, v0.z, v1.x, v1.z}, vhi[4] = {v0.y, v0.w, v1.y, v1.w};
+            RowRegs r[4];
+            uint32_t pos[4], bkt[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const uint32_t sport = (spw[i >> 1] >> (16 * (i & 1))) & 0xffffu;
+                const uint32_t dport = (dpw[i >> 1] >> (16 * (i & 1))) & 0xffffu;
+                r[i].a = pack64(dipv[i], sipv[i]);
+                r[i].b = pack64((sport << 16) | dport, fsv[i]);
+                r[i].proto = (pr >> (8 * i)) & 0xffu;
+                r[i].t = fev[i];
+                r[i].value = pack64(vlo[i], vhi[i]);
+                r[i].keep = row_keep(f, c, base + i, fsv[i], fev[i]);
+                const uint64_t h = key_hash(r[i].a, r[i].b, r[i].proto);
+                bkt[i] = bshift >= 64 ? 0u : (uint32_t)(h >> bshift);
+                r[i].proto |= hash_tag(h, bshift) << 8;
+                pos[i] = r[i].keep ? atomicAdd(&counters[bkt[i]], 1u) : 0xffffffffu;      // four atomics in flight
+            }
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                if (r[i].keep) place_row(r[i], bkt[i], pos[i], part, opt);
+        } else {
+            for (uint64_t i = base; i < R; i++) {
+                RowRegs r;
+                load_row_scalar(c, f, i, true, r);
+                emit_row<true>(r, bshift, counters, part, opt);
+            }
+        }
+    }
+}
+
 // ----------------------------------------------------------------------------------------
 // multi-CTA exclusive scans (bucket offsets; series base per bucket).  The grid never exceeds the
 // SM count with one 1024-thread CTA each, so all CTAs are co-resident and a CTA may spin on the
@@ -1325,7 +1384,17 @@ cudaError_t launch_scatter(cudaStream_t st, const ColPtrs &c, uint64_t R, const 
     if (R == 0) return cudaSuccess;
     const int bshift = 64 - logB;
     const OptScatter opt{slot_cap, ovf_cap, ovf, ovf_count};
-    if (cols_aligned16(c))
+    static std::atomic<int> rpt_s{0};
+    int rpt = rpt_s.load(std::memory_order_relaxed);
+    if (!rpt) {
+        const char *ev = getenv("TAD_SCATTER_RPT");           // rows per thread of the scatter: 8 (122 registers) or 4 (<= 64)
+        rpt = ev && atoi(ev) == 4 ? 4 : 8;
+        rpt_s.store(rpt, std::memory_order_relaxed);
+    }
+    if (rpt == 4 && cols_aligned16(c) && c.flow_end && c.value) {
+        const uint64_t want = ((R + 3) / 4 + 255) / 256, cap = (uint64_t)num_sms() * 4 * 4;
+        scatter4_kernel<<<(uint32_t)(want < cap ? (want ? want : 1) : cap), 256, 0, st>>>(c, R, f, bshift, cursor, part, opt);
+    } else if (cols_aligned16(c))
         partition_kernel<true, true><<<partition_grid(R), 256, 0, st>>>(c, R, f, bshift, cursor, part, opt);
     else
         partition_kernel<true, false><<<partition_grid(R), 256, 0, st>>>(c, R, f, bshift, cursor, part, opt);
