@@ -1522,8 +1522,8 @@ cudaError_t launch_detect_ewma(cudaStream_t st, const SeriesEntry *entries, cons
     static std::atomic<int> mode_s{-1};
     int mode = mode_s.load(std::memory_order_acquire);
     if (mode < 0) {
-        const char *ev = getenv("TAD_DETECT_MODE");          // 1 = direct (no stage, register-limited occupancy), 0 = TMA-staged
-        mode = ev ? atoi(ev) : 0;
+        const char *ev = getenv("TAD_DETECT_MODE");          // 1 = direct (no stage, register-limited occupancy; 0.63 vs 1.10 ms
+        mode = ev ? atoi(ev) : 1;                            // per 1e8 points, profiles/r02/ab2_summary.txt), 0 = TMA-staged
         mode_s.store(mode, std::memory_order_release);
     }
     if (mode == 1) {
