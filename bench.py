@@ -378,6 +378,7 @@ def run_ours(args):
         synth.make_flows_torch_sharded(S, n, seed=1, device=dev, rank=rank, world=world)
     rows = int(cols_t["value"].numel())
     torch.cuda.synchronize()
+    torch.cuda.empty_cache()         # the generator's temporaries go back to the driver: the engine allocates with cudaMalloc
     dcols = DeviceColumns(rows, {k: v.data_ptr() for k, v in cols_t.items()})
     dcols.keepalive = cols_t
 

@@ -463,7 +463,9 @@ void run_job(tad_ctx *ctx, tad_job *job)
     ensure(ctx->cls_list, (size_t)B * 4 * 3);
     ensure(ctx->nsb, (size_t)Bl * 4);
     ensure(ctx->npb, (size_t)Bl * 4);
-    ensure(ctx->part, (R ? R : 1) * sizeof(Row32));
+    // part[] (exact partition: 32 B per local row) is not needed when the multi-GPU optimistic path runs out of the exported
+    // slot buffer; the exact multi-GPU branch allocates it on demand
+    if (world == 1) ensure(ctx->part, (R ? R : 1) * sizeof(Row32));
     uint32_t *hist = (uint32_t *)ctx->hist.p, *offsets = (uint32_t *)ctx->offsets.p, *cursor = (uint32_t *)ctx->cursor.p;
     uint32_t *big_base = (uint32_t *)ctx->big_base.p;
     uint32_t *cls_list = (uint32_t *)ctx->cls_list.p;
@@ -689,6 +691,8 @@ void run_job(tad_ctx *ctx, tad_job *job)
             return v < R ? v : R;
         };
         const int NS = world * K;                              // segments: (source rank, chunk)
+        ensure(ctx->part, (R ? R : 1) * sizeof(Row32));
+        part = (Row32 *)ctx->part.p;
         ensure(ctx->hist, (size_t)B * 4 * K);
         ensure(ctx->offsets, ((size_t)B + 1) * 4 * K);
         ensure(ctx->cursor, (size_t)B * 4 * K);
