@@ -102,13 +102,13 @@ class ClockSampler:
 def ncu_traffic(kernel, rows):
     """dram bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/), valid for
     the 1e8-row workload it was taken on; None otherwise."""
-    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    try:
-        d = json.load(open(p))
-        if d.get("rows") == rows and kernel in d["kernels"]:
-            return d["kernels"][kernel]["dram_bytes_read"] + d["kernels"][kernel]["dram_bytes_write"]
-    except Exception:
-        pass
+    for name in ("r02_traffic.json", "r01_traffic.json"):          # newest capture of the shipped kernels first
+        try:
+            d = json.load(open(os.path.join(ROOT, "profiles", name)))
+            if d.get("rows") == rows and kernel in d["kernels"]:
+                return d["kernels"][kernel]["dram_bytes_read"] + d["kernels"][kernel]["dram_bytes_write"]
+        except Exception:
+            pass
     return None
 
 

@@ -80,12 +80,24 @@ def full_summary(src, dst, traffic_dst, title):
 
 
 if __name__ == "__main__":
-    launch_summary(os.path.join(G, "launches_r01_final.csv"), os.path.join(P, "r01_launches_final.txt"),
-                   "ncu --metrics gpu__time_duration.sum --clock-control none -c 100; python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e "
-                   "(1e8 rows / 1e6 connections, EWMA); round-1 final pipeline (optimistic partition). Per-launch times are cold-cache "
-                   "and serialised: compare SHARES with bench.py's phase_ms.")
-    full_summary(os.path.join(G, "prof_raw_final.csv"), os.path.join(P, "r01_ncu_full_final.txt"), os.path.join(P, "r01_traffic.json"),
-                 "ncu --set full --clock-control none --import-source on; bench.py --steps 1 --warmup 3 (1e8 rows); round-1 final pipeline "
-                 "(captured with the group kernel reading {bucket, rows, offset} from a 16-byte class-list entry; that variant was 0.08 ms "
-                 "slower inside the pipeline and the shipped kernel reads bucket_list + offsets[] again -- the kernel body is otherwise identical)")
-    print(open(os.path.join(P, "r01_launches_final.txt")).read()[:1800])
+    import sys
+    if len(sys.argv) > 1 and sys.argv[1] == "r02":
+        # round 2: gpurun_out/r02_launches.csv, r02_full_raw.csv (profiles/r02/prof.sh)
+        launch_summary(os.path.join(G, "r02_launches.csv"), os.path.join(P, "r02_launches.txt"),
+                       "ncu --metrics gpu__time_duration.sum --clock-control none -c 400: python bench.py --steps 2 --warmup 1 "
+                       "--no-cpu --no-e2e --no-parity --no-sides (1e8 rows, EWMA, B200, round-2 shipped build: optimistic scatter, "
+                       "three group classes, direct detector).  Per-launch times are cold-cache and serialised: compare SHARES.")
+        full_summary(os.path.join(G, "r02_full_raw.csv"), os.path.join(P, "r02_ncu_full.txt"), os.path.join(P, "r02_traffic.json"),
+                     "ncu --set full --clock-control none --import-source on (one job of the round-2 shipped build, 1e8 rows, B200)")
+        print(open(os.path.join(P, "r02_launches.txt")).read()[:1800])
+    else:
+
+        launch_summary(os.path.join(G, "launches_r01_final.csv"), os.path.join(P, "r01_launches_final.txt"),
+                       "ncu --metrics gpu__time_duration.sum --clock-control none -c 100; python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e "
+                       "(1e8 rows / 1e6 connections, EWMA); round-1 final pipeline (optimistic partition). Per-launch times are cold-cache "
+                       "and serialised: compare SHARES with bench.py's phase_ms.")
+        full_summary(os.path.join(G, "prof_raw_final.csv"), os.path.join(P, "r01_ncu_full_final.txt"), os.path.join(P, "r01_traffic.json"),
+                     "ncu --set full --clock-control none --import-source on; bench.py --steps 1 --warmup 3 (1e8 rows); round-1 final pipeline "
+                     "(captured with the group kernel reading {bucket, rows, offset} from a 16-byte class-list entry; that variant was 0.08 ms "
+                     "slower inside the pipeline and the shipped kernel reads bucket_list + offsets[] again -- the kernel body is otherwise identical)")
+        print(open(os.path.join(P, "r01_launches_final.txt")).read()[:1800])
