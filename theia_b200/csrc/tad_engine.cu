@@ -180,6 +180,7 @@ struct tad_ctx {
     // exported buffer (arrival counters in front, slots behind), the peers map it (CUDA IPC) and the owner's group kernel
     // pulls its bucket segments over NVLink -- no histogram pass, no all-to-all, no receive buffer.
     int peer_pull = 1;                              // TAD_PEER_PULL=0: always the exact partition + NCCL all-to-all
+    int exact_pull = 0;                             // TAD_EXACT_PULL=1: the exact partition is pulled by the peers too (no receive buffer)
     size_t x_budget = 72ull << 30;                  // largest exported slot buffer (TAD_SLOT_BUDGET_GB); beyond it: exact partition
     DevBuf xbuf;                                    // exported: [counters: B x u32, padded][slots: B x slot x Row32]
     void *peer_x[kMaxRanks]{};                      // peers' xbuf mapped into this process
@@ -544,6 +545,46 @@ void run_job(tad_ctx *ctx, tad_job *job)
         }
     }
 
+    // ---- exported buffer + peer mappings (multi-GPU peer pull) -----------------------------------------------------------
+    auto gather16 = [&]() {        // blocking 128-byte all-gather through pinned memory (rare: regrow, exact-path row counts)
+        CU(cudaMemcpyAsync(d_small, ctx->h_small, 16 * 8, cudaMemcpyHostToDevice, st));
+        if (nccl_allgather(&ctx->nccl, d_small, d_small + 16, 16 * 8, st)) fail(TAD_ERR_NCCL, "%s", nccl_last_error());
+        CU(cudaMemcpyAsync(ctx->h_small + 16, d_small + 16, 16 * 8 * world, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    };
+    // Every rank calls this with the SAME `need` in the same job (it depends only on values all ranks share), so all ranks
+    // regrow together: unmap, barrier (nobody maps a buffer that is about to be freed), reallocate, exchange the IPC
+    // handles, map.  First job or a larger table only.
+    auto ensure_exported = [&](size_t need) {
+        if (need <= ctx->xbuf.cap && ctx->peers_mapped) return;
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+        for (int r = 0; r < world; r++)
+            if (ctx->peer_x[r]) { CU(cudaIpcCloseMemHandle(ctx->peer_x[r])); ctx->peer_x[r] = nullptr; }
+        ctx->peers_mapped = false;
+        memset(ctx->h_small, 0, 16 * 8);
+        gather16();
+        ensure(ctx->xbuf, need);
+        cudaIpcMemHandle_t mine;
+        CU(cudaIpcGetMemHandle(&mine, ctx->xbuf.p));
+        memset(ctx->h_small, 0, 16 * 8);
+        ctx->h_small[0] = ctx->xbuf.cap;
+        memcpy(ctx->h_small + 2, &mine, sizeof(mine));
+        gather16();
+        for (int r = 0; r < world; r++) {
+            if (r == me) continue;
+            cudaIpcMemHandle_t h;
+            memcpy(&h, ctx->h_small + 16 + 16 * r + 2, sizeof(h));
+            if (ctx->h_small[16 + 16 * r] < need) fail(TAD_ERR_INTERNAL, "rank %d exports a smaller partition buffer", r);
+            cudaError_t e = cudaIpcOpenMemHandle(&ctx->peer_x[r], h, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                ctx->peer_x[r] = nullptr;
+                fail(TAD_ERR_CUDA, "cannot map the partition buffer of rank %d (%s); set TAD_PEER_PULL=0 on every rank to "
+                                   "exchange rows through NCCL instead", r, cudaGetErrorString(e));
+            }
+        }
+        ctx->peers_mapped = true;
+    };
     // ---- several GPUs, optimistic partition + peer pull ---------------------------------------------------------------
     // Every rank scatters its rows into fixed-capacity slots of ALL global buckets (slot = kGroupCap / world rows: a
     // source holds 1/world of a bucket on average) inside a buffer its peers have mapped with CUDA IPC.  One 8-byte
@@ -557,44 +598,7 @@ void run_job(tad_ctx *ctx, tad_job *job)
     bool sync_at_end = false;
     if (world > 1 && ctx->peer_pull && ctx->optimistic && R_total > 0 && (uint64_t)B * slotM <= (1ull << 31) &&
         x_need <= ctx->x_budget) {
-        auto gather16 = [&]() {        // blocking 128-byte all-gather through pinned memory (regrow only)
-            CU(cudaMemcpyAsync(d_small, ctx->h_small, 16 * 8, cudaMemcpyHostToDevice, st));
-            if (nccl_allgather(&ctx->nccl, d_small, d_small + 16, 16 * 8, st)) fail(TAD_ERR_NCCL, "%s", nccl_last_error());
-            CU(cudaMemcpyAsync(ctx->h_small + 16, d_small + 16, 16 * 8 * world, cudaMemcpyDeviceToHost, st));
-            CU(cudaStreamSynchronize(st));
-        };
-        if (x_need > ctx->xbuf.cap || !ctx->peers_mapped) {
-            // Regrow (first job, or a larger table).  x_need depends only on the global bucket count, so every rank
-            // takes this branch in the same job: unmap, barrier (nobody maps a buffer that is about to be freed),
-            // reallocate, exchange the IPC handles, map.
-            static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
-            for (int r = 0; r < world; r++)
-                if (ctx->peer_x[r]) { CU(cudaIpcCloseMemHandle(ctx->peer_x[r])); ctx->peer_x[r] = nullptr; }
-            ctx->peers_mapped = false;
-            memset(ctx->h_small, 0, 16 * 8);
-            gather16();
-            ensure(ctx->xbuf, x_need);
-            cudaIpcMemHandle_t mine;
-            CU(cudaIpcGetMemHandle(&mine, ctx->xbuf.p));
-            memset(ctx->h_small, 0, 16 * 8);
-            ctx->h_small[0] = ctx->xbuf.cap;
-            memcpy(ctx->h_small + 2, &mine, sizeof(mine));
-            gather16();
-            for (int r = 0; r < world; r++) {
-                if (r == me) continue;
-                cudaIpcMemHandle_t h;
-                memcpy(&h, ctx->h_small + 16 + 16 * r + 2, sizeof(h));
-                if (ctx->h_small[16 + 16 * r] < x_need) fail(TAD_ERR_INTERNAL, "rank %d exports a smaller partition buffer", r);
-                cudaError_t e = cudaIpcOpenMemHandle(&ctx->peer_x[r], h, cudaIpcMemLazyEnablePeerAccess);
-                if (e != cudaSuccess) {
-                    cudaGetLastError();
-                    ctx->peer_x[r] = nullptr;
-                    fail(TAD_ERR_CUDA, "cannot map the partition buffer of rank %d (%s); set TAD_PEER_PULL=0 on every rank to "
-                                       "exchange rows through NCCL instead", r, cudaGetErrorString(e));
-                }
-            }
-            ctx->peers_mapped = true;
-        }
+        ensure_exported(x_need);
         uint32_t *xcursor = static_cast<uint32_t *>(ctx->xbuf.p);
         Row32 *xpart = reinterpret_cast<Row32 *>(static_cast<char *>(ctx->xbuf.p) + x_cnt_bytes);
         ensure(ctx->xcnt, (size_t)Bl * 4 * world);
@@ -683,7 +687,10 @@ void run_job(tad_ctx *ctx, tad_job *job)
         // ---- multi GPU, exact partition: K row chunks; chunk c is sent over NVLink (comm stream) while chunk c+1 is scattered ------
         // chunked (overlapped) exchange pays off at N = 2 (measured 11.5 -> 9.6 ms); at N >= 4 the NVLink all-to-all is
         // longer than the scatter it could hide behind and the extra segments cost the group kernel more than is won
-        const int K = (R >= ctx->exchange_min_rows && (world == 2 || ctx->exchange_chunks_forced)) ? ctx->exchange_chunks : 1;
+        // With peer pull (default) the exact partition is written into the EXPORTED buffer and the owners' group kernels read
+        // their segments straight out of the peers' copies: no receive buffer, no all-to-all (and no chunking: K = 1).
+        const bool pull = ctx->peer_pull != 0 && ctx->exact_pull != 0;
+        const int K = pull ? 1 : (R >= ctx->exchange_min_rows && (world == 2 || ctx->exchange_chunks_forced)) ? ctx->exchange_chunks : 1;
         auto xlo = [&](int cidx) -> uint64_t {
             if (cidx <= 0) return 0;
             if (cidx >= K) return R;
@@ -691,8 +698,20 @@ void run_job(tad_ctx *ctx, tad_job *job)
             return v < R ? v : R;
         };
         const int NS = world * K;                              // segments: (source rank, chunk)
-        ensure(ctx->part, (R ? R : 1) * sizeof(Row32));
-        part = (Row32 *)ctx->part.p;
+        if (pull) {
+            // the exported buffer must hold the largest shard: the ranks agree on it (blocking 128-byte all-gather; this path
+            // is the fallback for skewed or very large tables, where a host sync more does not matter)
+            memset(ctx->h_small, 0, 16 * 8);
+            ctx->h_small[0] = R;
+            gather16();
+            uint64_t max_rows = 1;
+            for (int r = 0; r < world; r++) max_rows = std::max<uint64_t>(max_rows, ctx->h_small[16 + 16 * r]);
+            ensure_exported(x_cnt_bytes + max_rows * sizeof(Row32));
+            part = reinterpret_cast<Row32 *>(static_cast<char *>(ctx->xbuf.p) + x_cnt_bytes);
+        } else {
+            ensure(ctx->part, (R ? R : 1) * sizeof(Row32));
+            part = (Row32 *)ctx->part.p;
+        }
         ensure(ctx->hist, (size_t)B * 4 * K);
         ensure(ctx->offsets, ((size_t)B + 1) * 4 * K);
         ensure(ctx->cursor, (size_t)B * 4 * K);
@@ -718,8 +737,9 @@ void run_job(tad_ctx *ctx, tad_job *job)
         mark(TAD_PHASE_SCAN);
         // every rank learns every (rank, chunk) histogram: segment offsets of the owned bucket range, receive sizes
         if (nccl_allgather(&ctx->nccl, hist, hist_all, (size_t)B * 4 * K, st)) fail(TAD_ERR_NCCL, "%s", nccl_last_error());
-        CU(launch_segment_scan(st, hist_all, B, b_lo, Bl, NS, seg_off, seg_total, d_small)); launches += 2;
+        CU(launch_segment_scan(st, hist_all, B, b_lo, Bl, NS, seg_off, seg_total, d_small, pull ? d_small + 40 : nullptr)); launches += 2;
         CU(cudaMemcpyAsync(ctx->h_small, d_small, 8 * NS, cudaMemcpyDeviceToHost, st));
+        if (pull) CU(cudaMemcpyAsync(ctx->h_small + 40, d_small + 40, 8 * NS, cudaMemcpyDeviceToHost, st));
         for (int cx = 0; cx < K; cx++)        // send boundaries of chunk cx: offsets_cx[p * Bl], p = 0..world
             CU(cudaMemcpy2DAsync(ctx->h_small + 64 + cx * (kMaxRanks + 1), 8, offsets + (size_t)cx * (B + 1), (size_t)Bl * 4, 4,
                                  world + 1, cudaMemcpyDeviceToHost, st));
@@ -736,8 +756,22 @@ void run_job(tad_ctx *ctx, tad_job *job)
             kept += send_lo[cx][world];
         }
         if (owned >= (1ull << 32) - 1) fail(TAD_ERR_INVALID_ARG, "more than 2^32-2 rows owned by one GPU after the exchange");
-        ensure(ctx->exch, recv_total ? recv_total : 32);
         cudaStream_t cs = ctx->copy_stream;
+        if (pull) {
+            CU(launch_scatter(st, c, R, f, logB, cursor, part)); launches += R ? 1 : 0;
+            mark(TAD_PHASE_SCATTER);
+            // barrier: every rank's exact partition is complete
+            if (nccl_allgather(&ctx->nccl, d_small + 48, d_small + 56, 8, st)) fail(TAD_ERR_NCCL, "%s", nccl_last_error());
+            mark(TAD_PHASE_SYNC);
+            seg.nseg = world;
+            for (int r = 0; r < world; r++) {
+                const char *xb = r == me ? static_cast<const char *>(ctx->xbuf.p) : static_cast<const char *>(ctx->peer_x[r]);
+                seg.base[r] = reinterpret_cast<const Row32 *>(xb + x_cnt_bytes) + ctx->h_small[40 + r];   // rows in front of my range
+                seg.off[r] = seg_off + (size_t)r * (Bl + 1);
+            }
+            sync_at_end = true;
+        } else {
+        ensure(ctx->exch, recv_total ? recv_total : 32);
         for (int cx = 0; cx < K; cx++) {
             const uint64_t lo = xlo(cx), hi = xlo(cx + 1);
             if (hi > lo) { CU(launch_scatter(st, offset_cols(lo), hi - lo, f, logB, cursor + (size_t)cx * B, part + lo)); launches++; }
@@ -761,6 +795,7 @@ void run_job(tad_ctx *ctx, tad_job *job)
             seg.base[sgi] = r == me ? part + xlo(cx) + send_lo[cx][me]
                                     : reinterpret_cast<const Row32 *>((const char *)ctx->exch.p + recv_off[sgi]);
             seg.off[sgi] = seg_off + (size_t)sgi * (Bl + 1);
+        }
         }
         // final (virtual) bucket offsets of the owned range, oversized-bucket list, capacity-class lists
         CU(launch_bucket_scan(st, seg_total, offsets, cursor, Bl, kGroupCap, big_list, big_base, cls_list, d_stats,
@@ -1046,6 +1081,7 @@ int tad_init(const tad_config *cfg, tad_ctx **out)
     for (int i = 0; ok && i <= kMaxXChunks; i++) ok = cudaEventCreateWithFlags(&ctx->x_ev[i], cudaEventDisableTiming) == cudaSuccess;
     if (const char *e = getenv("TAD_OPTIMISTIC")) ctx->optimistic = atoi(e);
     if (const char *e = getenv("TAD_PEER_PULL")) ctx->peer_pull = atoi(e);
+    if (const char *e = getenv("TAD_EXACT_PULL")) ctx->exact_pull = atoi(e);
     if (const char *e = getenv("TAD_SLOT_BUDGET_GB")) ctx->x_budget = (size_t)strtoull(e, nullptr, 10) << 30;
     if (const char *e = getenv("TAD_EXCHANGE_MIN_ROWS")) ctx->exchange_min_rows = strtoull(e, nullptr, 10);
     if (getenv("TAD_EXCHANGE_CHUNKS")) ctx->exchange_chunks_forced = true;

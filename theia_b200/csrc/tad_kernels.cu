@@ -1559,10 +1559,25 @@ cudaError_t launch_detect_dbscan(cudaStream_t st, const SeriesEntry *entries, co
 // ----------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) segment_scan_kernel(const uint32_t *__restrict__ hist_all, uint32_t B_global, uint32_t b_lo,
                                                             uint32_t B_local, uint32_t *__restrict__ seg_off,
-                                                            unsigned long long *__restrict__ seg_rows)
+                                                            unsigned long long *__restrict__ seg_rows,
+                                                            unsigned long long *__restrict__ seg_before /* may be null */)
 {
     __shared__ uint32_t total_s;
+    __shared__ unsigned long long before_s;
     const uint32_t r = blockIdx.x;
+    if (seg_before) {
+        // rows of source segment r that sit in front of this rank's bucket range inside r's (bucket-ordered) partition
+        // buffer: where the peer-pull group kernel starts reading
+        if (threadIdx.x == 0) before_s = 0ull;
+        __syncthreads();
+        const uint32_t *hb = hist_all + (size_t)r * B_global;
+        unsigned long long acc = 0;
+        for (uint32_t i = threadIdx.x; i < b_lo; i += 1024) acc += hb[i];
+        for (int d = 16; d; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+        if ((threadIdx.x & 31) == 0 && acc) atomicAdd(&before_s, acc);
+        __syncthreads();
+        if (threadIdx.x == 0) seg_before[r] = before_s;
+    }
     const uint32_t *h = hist_all + (size_t)r * B_global + b_lo;
     uint32_t *out = seg_off + (size_t)r * (B_local + 1);
     const uint32_t per = (B_local + 1023) / 1024;
@@ -1636,9 +1651,10 @@ cudaError_t launch_gather_counts(cudaStream_t st, const PeerCounters &pc, int wo
 }
 
 cudaError_t launch_segment_scan(cudaStream_t st, const uint32_t *hist_all, uint32_t B_global, uint32_t b_lo, uint32_t B_local,
-                                int nseg, uint32_t *seg_off, uint32_t *total, unsigned long long *seg_rows)
+                                int nseg, uint32_t *seg_off, uint32_t *total, unsigned long long *seg_rows,
+                                unsigned long long *seg_before)
 {
-    segment_scan_kernel<<<nseg, 1024, 0, st>>>(hist_all, B_global, b_lo, B_local, seg_off, seg_rows);
+    segment_scan_kernel<<<nseg, 1024, 0, st>>>(hist_all, B_global, b_lo, B_local, seg_off, seg_rows, seg_before);
     const uint32_t grid = (B_local + 255) / 256;
     segment_total_kernel<<<grid > 1184 ? 1184 : grid, 256, 0, st>>>(hist_all, B_global, b_lo, B_local, nseg, total);
     return cudaGetLastError();

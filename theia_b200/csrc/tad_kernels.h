@@ -64,5 +64,6 @@ cudaError_t launch_gather_counts(cudaStream_t st, const PeerCounters &pc, int wo
 // all-gathered histograms.  hist_all[r * B_global + b]; range = [b_lo, b_lo + B_local).
 cudaError_t launch_segment_scan(cudaStream_t st, const uint32_t *hist_all, uint32_t B_global, uint32_t b_lo, uint32_t B_local,
                                 int nseg, uint32_t *seg_off /* nseg x (B_local+1) */, uint32_t *total /* B_local */,
-                                unsigned long long *seg_rows /* nseg */);
+                                unsigned long long *seg_rows /* nseg */,
+                                unsigned long long *seg_before = nullptr /* nseg: rows of each source in front of the owned range */);
 }
