@@ -9,7 +9,8 @@ mode = gpu : every rank runs its row shard of every case through the engine and 
                         exchange; asserted through phase_ms)
                skewed : two long connections sit on the last rank -> a slot overflows there, every rank falls back to
                         the exact partition + NCCL all-to-all (chunked, overlapped)
-               nccl   : the spread table with the peer pull switched off (second engine)"""
+               xpull  : the skewed table with TAD_EXACT_PULL=1: the fallback's exact partition is pulled by the peers as well
+               nccl   : the spread table with the peer pull switched off (third engine)"""
 import os
 import sys
 
@@ -80,6 +81,19 @@ def main():
                     assert optimistic == (name == "spread"), (rank, name, st["phase_ms"])
                     np.savez(os.path.join(out_dir, "res_%s_%s_%d.npz" % (name, algo, rank)), **got)
         eng.close()
+        # the exact partition pulled by the peers (no receive buffer): the skewed table overflows a slot, every rank falls back
+        os.environ["TAD_EXACT_PULL"] = "1"
+        eng = engine(True)
+        table = case_table("skewed")
+        total = len(table["value"])
+        mine = sharding.shard_rows(table, rank, world)
+        for algo in ("EWMA", "DBSCAN"):
+            for rep in range(2):
+                got, st = eng.run(mine, algo=algo, tad_id="multi", emit_all=True, global_rows=total)
+            assert st["phase_ms"]["hist"] > 0.0 and st["rows_kept"] == len(mine["value"])
+            np.savez(os.path.join(out_dir, "res_xpull_%s_%d.npz" % (algo, rank)), **got)
+        eng.close()
+        os.environ["TAD_EXACT_PULL"] = "0"
         eng = engine(False)
         table = case_table("spread")
         mine = sharding.shard_rows(table, rank, world)
