@@ -180,6 +180,8 @@ struct tad_ctx {
     // exported buffer (arrival counters in front, slots behind), the peers map it (CUDA IPC) and the owner's group kernel
     // pulls its bucket segments over NVLink -- no histogram pass, no all-to-all, no receive buffer.
     int peer_pull = 1;                              // TAD_PEER_PULL=0: always the exact partition + NCCL all-to-all
+    GroupStreams gstreams{};                        // side streams of the group phase (capacity classes run concurrently)
+    int group_concurrent = 0;                       // TAD_GROUP_CONCURRENT=1
     int exact_pull = 0;                             // TAD_EXACT_PULL=1: the exact partition is pulled by the peers too (no receive buffer)
     size_t x_budget = 72ull << 30;                  // largest exported slot buffer (TAD_SLOT_BUDGET_GB); beyond it: exact partition
     DevBuf xbuf;                                    // exported: [counters: B x u32, padded][slots: B x slot x Row32]
@@ -826,7 +828,8 @@ void run_job(tad_ctx *ctx, tad_job *job)
     {
         int l = 0;
         const uint32_t n_cls[3] = {ctx->h_stats[ST_NCLS0], ctx->h_stats[ST_NCLS1], ctx->h_stats[ST_NCLS2]};
-        CU(launch_group(st, seg, entries, offsets, Bl, logB, cls_list, n_cls, csr_v, csr_t, csr_p, nsb, npb, sp.reducer, &l));
+        CU(launch_group(st, seg, entries, offsets, Bl, logB, cls_list, n_cls, csr_v, csr_t, csr_p, nsb, npb, sp.reducer, &l,
+                        ctx->group_concurrent ? &ctx->gstreams : nullptr));
         launches += l;
     }
     mark(TAD_PHASE_GROUP);
@@ -1082,6 +1085,12 @@ int tad_init(const tad_config *cfg, tad_ctx **out)
     if (const char *e = getenv("TAD_OPTIMISTIC")) ctx->optimistic = atoi(e);
     if (const char *e = getenv("TAD_PEER_PULL")) ctx->peer_pull = atoi(e);
     if (const char *e = getenv("TAD_EXACT_PULL")) ctx->exact_pull = atoi(e);
+    if (const char *e = getenv("TAD_GROUP_CONCURRENT")) ctx->group_concurrent = atoi(e);
+    for (int i = 0; ok && i < 2; i++) {
+        ok = cudaStreamCreateWithFlags(&ctx->gstreams.aux[i], cudaStreamNonBlocking) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&ctx->gstreams.join[i], cudaEventDisableTiming) == cudaSuccess;
+    }
+    ok = ok && cudaEventCreateWithFlags(&ctx->gstreams.fork, cudaEventDisableTiming) == cudaSuccess;
     if (const char *e = getenv("TAD_SLOT_BUDGET_GB")) ctx->x_budget = (size_t)strtoull(e, nullptr, 10) << 30;
     if (const char *e = getenv("TAD_EXCHANGE_MIN_ROWS")) ctx->exchange_min_rows = strtoull(e, nullptr, 10);
     if (getenv("TAD_EXCHANGE_CHUNKS")) ctx->exchange_chunks_forced = true;
@@ -1142,6 +1151,11 @@ void tad_shutdown(tad_ctx *ctx)
     if (ctx->start_ev) cudaEventDestroy(ctx->start_ev);
     for (int i = 0; i <= kMaxXChunks; i++)
         if (ctx->x_ev[i]) cudaEventDestroy(ctx->x_ev[i]);
+    for (int i = 0; i < 2; i++) {
+        if (ctx->gstreams.join[i]) cudaEventDestroy(ctx->gstreams.join[i]);
+        if (ctx->gstreams.aux[i]) cudaStreamDestroy(ctx->gstreams.aux[i]);
+    }
+    if (ctx->gstreams.fork) cudaEventDestroy(ctx->gstreams.fork);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;

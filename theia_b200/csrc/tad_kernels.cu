@@ -1444,9 +1444,10 @@ static cudaError_t launch_group_class(cudaStream_t st, const SegDesc &seg, Serie
 // listed bucket -- launching all B CTAs per class and exiting early costs ~0.5 ms per class at 180 KB of shared
 // memory per CTA.  Empty buckets keep the zeroes the caller memset into nsb / npb.
 template <bool VRANK>
-static cudaError_t launch_group_all(cudaStream_t st, const SegDesc &seg, SeriesEntry *entries, const uint32_t *offsets,
-                                    uint32_t B, const uint32_t *cls_list, const uint32_t n_cls[3], uint64_t *csr_v,
-                                    uint32_t *csr_t, uint32_t *csr_p, uint32_t *nsb, uint32_t *npb, int reducer, int *launches)
+static cudaError_t launch_group_all(cudaStream_t st, const GroupStreams *gs, const SegDesc &seg, SeriesEntry *entries,
+                                    const uint32_t *offsets, uint32_t B, const uint32_t *cls_list, const uint32_t n_cls[3],
+                                    uint64_t *csr_v, uint32_t *csr_t, uint32_t *csr_p, uint32_t *nsb, uint32_t *npb, int reducer,
+                                    int *launches)
 {
     static std::atomic<int> small_nt_s{0};
     int small_nt = small_nt_s.load(std::memory_order_relaxed);
@@ -1456,33 +1457,50 @@ static cudaError_t launch_group_all(cudaStream_t st, const SegDesc &seg, SeriesE
         small_nt_s.store(small_nt, std::memory_order_relaxed);
     }
     *launches = 0;
-    cudaError_t e = small_nt == 128
-                        ? launch_group_class<kGroupCapSmall, 128, VRANK>(st, seg, entries, offsets, cls_list, n_cls[0], 0,
-                                                                         csr_v, csr_t, csr_p, nsb, npb, reducer)
-                        : launch_group_class<kGroupCapSmall, 256, VRANK>(st, seg, entries, offsets, cls_list, n_cls[0], 0,
-                                                                         csr_v, csr_t, csr_p, nsb, npb, reducer);
-    *launches += n_cls[0] ? 1 : 0;
+    // The three classes work on disjoint buckets.  With `gs` the two large classes (one or two CTAs per SM by shared memory)
+    // run on side streams NEXT TO the first class instead of after it: their few big CTAs start first, the small CTAs fill
+    // the rest of every SM, and the low-occupancy tails of the three launches overlap.
+    cudaStream_t s1 = st, s2 = st;
+    const bool fork = gs != nullptr && (n_cls[1] || n_cls[2]);
+    cudaError_t e = cudaSuccess;
+    if (fork) {
+        e = cudaEventRecord(gs->fork, st);
+        if (e == cudaSuccess && n_cls[1]) { s1 = gs->aux[0]; e = cudaStreamWaitEvent(s1, gs->fork, 0); }
+        if (e == cudaSuccess && n_cls[2]) { s2 = gs->aux[1]; e = cudaStreamWaitEvent(s2, gs->fork, 0); }
+    }
+    if (e == cudaSuccess && n_cls[2]) {
+        e = launch_group_class<kGroupCap, 512, VRANK>(s2, seg, entries, offsets, cls_list + 2 * (size_t)B, n_cls[2], kGroupCapMid,
+                                                      csr_v, csr_t, csr_p, nsb, npb, reducer);
+        ++*launches;
+    }
     if (e == cudaSuccess && n_cls[1]) {
-        e = launch_group_class<kGroupCapMid, 256, VRANK>(st, seg, entries, offsets, cls_list + B, n_cls[1], kGroupCapSmall,
+        e = launch_group_class<kGroupCapMid, 256, VRANK>(s1, seg, entries, offsets, cls_list + B, n_cls[1], kGroupCapSmall,
                                                          csr_v, csr_t, csr_p, nsb, npb, reducer);
         ++*launches;
     }
-    if (e == cudaSuccess && n_cls[2]) {
-        e = launch_group_class<kGroupCap, 512, VRANK>(st, seg, entries, offsets, cls_list + 2 * (size_t)B, n_cls[2], kGroupCapMid,
-                                                      csr_v, csr_t, csr_p, nsb, npb, reducer);
-        ++*launches;
+    if (e == cudaSuccess) {
+        e = small_nt == 128
+                ? launch_group_class<kGroupCapSmall, 128, VRANK>(st, seg, entries, offsets, cls_list, n_cls[0], 0, csr_v, csr_t,
+                                                                 csr_p, nsb, npb, reducer)
+                : launch_group_class<kGroupCapSmall, 256, VRANK>(st, seg, entries, offsets, cls_list, n_cls[0], 0, csr_v, csr_t,
+                                                                 csr_p, nsb, npb, reducer);
+        *launches += n_cls[0] ? 1 : 0;
+    }
+    if (fork) {          // join: the main stream continues when all classes are done (also after an error above)
+        if (n_cls[1]) { cudaEventRecord(gs->join[0], s1); cudaStreamWaitEvent(st, gs->join[0], 0); }
+        if (n_cls[2]) { cudaEventRecord(gs->join[1], s2); cudaStreamWaitEvent(st, gs->join[1], 0); }
     }
     return e;
 }
 
 cudaError_t launch_group(cudaStream_t st, const SegDesc &seg, SeriesEntry *entries, const uint32_t *offsets, uint32_t B,
                          int logB, const uint32_t *cls_list, const uint32_t n_cls[3], uint64_t *csr_v, uint32_t *csr_t,
-                         uint32_t *csr_p, uint32_t *nsb, uint32_t *npb, int reducer, int *launches)
+                         uint32_t *csr_p, uint32_t *nsb, uint32_t *npb, int reducer, int *launches, const GroupStreams *gs)
 {
     (void)logB;        // the slot hash bits travel with the rows (hash_tag)
-    return csr_p ? launch_group_all<true>(st, seg, entries, offsets, B, cls_list, n_cls, csr_v, csr_t, csr_p, nsb, npb,
+    return csr_p ? launch_group_all<true>(st, gs, seg, entries, offsets, B, cls_list, n_cls, csr_v, csr_t, csr_p, nsb, npb,
                                           reducer, launches)
-                 : launch_group_all<false>(st, seg, entries, offsets, B, cls_list, n_cls, csr_v, csr_t, csr_p, nsb, npb,
+                 : launch_group_all<false>(st, gs, seg, entries, offsets, B, cls_list, n_cls, csr_v, csr_t, csr_p, nsb, npb,
                                            reducer, launches);
 }
 
