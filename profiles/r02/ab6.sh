@@ -1,0 +1,25 @@
+#!/bin/bash
+# round 2, GPU call 6 (2 GPUs): exact partition + peer pull (dense remote reads), concurrent group classes
+set -u
+mkdir -p gpurun_out
+timeout 500 python -m pytest tests/test_multi_rank.py -m gpu -x -q -s > gpurun_out/ab6_tests.log 2>&1; echo "rc=$?" >> gpurun_out/ab6_tests.log
+tail -4 gpurun_out/ab6_tests.log
+T="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29701 bench.py --gpus 2 --steps 10 --warmup 3 --no-cpu --no-e2e"
+TAD_OPTIMISTIC=0 TAD_EXACT_PULL=1 timeout 300 $T > gpurun_out/ab6_n2_xpull.json 2> gpurun_out/ab6_n2_xpull.err
+timeout 300 $T > gpurun_out/ab6_n2_pull.json 2> gpurun_out/ab6_n2_pull.err
+TAD_GROUP_CONCURRENT=1 timeout 300 $T > gpurun_out/ab6_n2_pull_conc.json 2> gpurun_out/ab6_n2_pull_conc.err
+B="timeout 120 python bench.py --no-cpu --no-e2e --no-sides --steps 10 --warmup 3"
+TAD_GROUP_CONCURRENT=1 $B > gpurun_out/ab6_n1_conc.json 2> gpurun_out/ab6_n1_conc.err
+$B > gpurun_out/ab6_n1.json 2> gpurun_out/ab6_n1.err
+TAD_GROUP_CONCURRENT=1 $B > gpurun_out/ab6_n1_conc2.json 2> gpurun_out/ab6_n1_conc2.err
+TAD_GROUP_CONCURRENT=1 timeout 300 python -m pytest tests/test_gpu_parity.py tests/test_gpu_full_size.py -m gpu -x -q > gpurun_out/ab6_tests_conc.log 2>&1; echo "rc=$?" >> gpurun_out/ab6_tests_conc.log
+tail -3 gpurun_out/ab6_tests_conc.log
+python - <<'PY'
+import json, glob
+for p in sorted(glob.glob("gpurun_out/ab6_*.json")):
+    try:
+        d = json.loads(open(p).read().strip().splitlines()[-1])
+        print("%-26s value %.3e  %.3f ms" % (p.split("/")[-1], d["value"], d["ms_per_step"]), {k: round(v, 3) for k, v in d["phase_ms"].items() if v}, (d.get("parity") or {}).get("ok"))
+    except Exception as e:
+        print(p, "n/a", e)
+PY
