@@ -182,6 +182,8 @@ struct tad_ctx {
     int peer_pull = 1;                              // TAD_PEER_PULL=0: always the exact partition + NCCL all-to-all
     GroupStreams gstreams{};                        // side streams of the group phase (capacity classes run concurrently)
     int group_concurrent = 0;                       // TAD_GROUP_CONCURRENT=1
+    int sort_classes = 0;                           // TAD_SORT_CLASSES=1: capacity-class bucket lists sorted by bucket before the group phase
+    DevBuf sortb;
     int exact_pull = 0;                             // TAD_EXACT_PULL=1: the exact partition is pulled by the peers too (no receive buffer)
     size_t x_budget = 72ull << 30;                  // largest exported slot buffer (TAD_SLOT_BUDGET_GB); beyond it: exact partition
     DevBuf xbuf;                                    // exported: [counters: B x u32, padded][slots: B x slot x Row32]
@@ -828,6 +830,15 @@ void run_job(tad_ctx *ctx, tad_job *job)
     {
         int l = 0;
         const uint32_t n_cls[3] = {ctx->h_stats[ST_NCLS0], ctx->h_stats[ST_NCLS1], ctx->h_stats[ST_NCLS2]};
+        if (ctx->sort_classes) {
+            // class lists in ascending bucket order: concurrently running CTAs then touch neighbouring slots / csr stretches
+            const size_t need = sort_lists_scratch_bytes(Bl);
+            ensure(ctx->sortb, need);
+            int bits = 1;
+            while ((1u << bits) < Bl && bits < 32) bits++;
+            for (int k = 0; k < 3; k++)
+                if (n_cls[k] > 1) { CU(sort_bucket_list(st, cls_list + (size_t)k * Bl, n_cls[k], bits, ctx->sortb.p, ctx->sortb.cap)); launches += 3; }
+        }
         CU(launch_group(st, seg, entries, offsets, Bl, logB, cls_list, n_cls, csr_v, csr_t, csr_p, nsb, npb, sp.reducer, &l,
                         ctx->group_concurrent ? &ctx->gstreams : nullptr));
         launches += l;
@@ -1085,6 +1096,7 @@ int tad_init(const tad_config *cfg, tad_ctx **out)
     if (const char *e = getenv("TAD_OPTIMISTIC")) ctx->optimistic = atoi(e);
     if (const char *e = getenv("TAD_PEER_PULL")) ctx->peer_pull = atoi(e);
     if (const char *e = getenv("TAD_EXACT_PULL")) ctx->exact_pull = atoi(e);
+    if (const char *e = getenv("TAD_SORT_CLASSES")) ctx->sort_classes = atoi(e);
     if (const char *e = getenv("TAD_GROUP_CONCURRENT")) ctx->group_concurrent = atoi(e);
     for (int i = 0; ok && i < 2; i++) {
         ok = cudaStreamCreateWithFlags(&ctx->gstreams.aux[i], cudaStreamNonBlocking) == cudaSuccess;
@@ -1133,7 +1145,7 @@ void tad_shutdown(tad_ctx *ctx)
         ctx->peers_mapped = false;
     }
     nccl_comm_destroy(&ctx->nccl);
-    DevBuf *bufs[] = {&ctx->xbuf, &ctx->xcnt, &ctx->xtotal, &ctx->hist, &ctx->offsets, &ctx->cursor, &ctx->big_list, &ctx->big_base, &ctx->cls_list, &ctx->csr_p, &ctx->stats, &ctx->part, &ctx->csr_v,
+    DevBuf *bufs[] = {&ctx->xbuf, &ctx->xcnt, &ctx->xtotal, &ctx->sortb, &ctx->hist, &ctx->offsets, &ctx->cursor, &ctx->big_list, &ctx->big_base, &ctx->cls_list, &ctx->csr_p, &ctx->stats, &ctx->part, &ctx->csr_v,
                       &ctx->csr_t, &ctx->nsb, &ctx->npb, &ctx->sbase, &ctx->outb, &ctx->ns_ignore, &ctx->spill, &ctx->dbx,
                       &ctx->dbi, &ctx->exch, &ctx->scan_sync, &ctx->small, &ctx->hist_all, &ctx->seg_off, &ctx->seg_total,
                       &ctx->entries, &ctx->ar_y, &ctx->ar_pred, &ctx->ar_lam, &ctx->ovf};

@@ -50,6 +50,9 @@ cudaError_t launch_detect_arima(cudaStream_t st, const SeriesEntry *entries, con
 // same per-series arrays / in-place series entries / nsb / npb the group kernel produces.
 // `scratch` must hold spill_scratch_bytes(big_rows) bytes.  Returns launches through *launches.
 size_t spill_scratch_bytes(uint64_t big_rows);
+// Sort a capacity-class bucket list ascending (CUB radix sort over `key_bits` bits); scratch from sort_lists_scratch_bytes(max n).
+size_t sort_lists_scratch_bytes(uint32_t max_items);
+cudaError_t sort_bucket_list(cudaStream_t st, uint32_t *list, uint32_t n, int key_bits, void *scratch, size_t scratch_bytes);
 // Optimistic partition (seg.stride != 0): a listed bucket holds min(count, stride) rows in its slot and the rest in
 // ovf[0, n_ovf) (every overflow row belongs to a listed bucket).
 cudaError_t run_spill(cudaStream_t st, const SegDesc &seg, SeriesEntry *entries, const uint32_t *offsets, const uint32_t *big_list,

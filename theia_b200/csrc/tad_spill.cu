@@ -207,4 +207,28 @@ cudaError_t run_spill(cudaStream_t st, const SegDesc &seg, SeriesEntry *entries,
     return cudaGetLastError();
 }
 
+// ----------------------------------------------------------------------------------------------------------------
+// Capacity-class bucket lists in ascending bucket order.  The bucket scan appends to them with atomics, i.e. in no particular
+// order; sorted, the CTAs that run at the same time work on neighbouring buckets -- neighbouring slots of the partition buffer
+// (local, and over NVLink the peers') and neighbouring stretches of the csr arrays -- instead of 600 random places.
+// ----------------------------------------------------------------------------------------------------------------
+size_t sort_lists_scratch_bytes(uint32_t max_items)
+{
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)max_items, 0, 32);
+    return align256(bytes) + align256((size_t)max_items * 4) + 256;
+}
+
+cudaError_t sort_bucket_list(cudaStream_t st, uint32_t *list, uint32_t n, int key_bits, void *scratch, size_t scratch_bytes)
+{
+    if (n < 2) return cudaSuccess;
+    size_t temp_bytes = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, temp_bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)n, 0, key_bits);
+    if (align256(temp_bytes) + (size_t)n * 4 > scratch_bytes) return cudaErrorInvalidValue;
+    uint32_t *tmp = reinterpret_cast<uint32_t *>(static_cast<char *>(scratch) + align256(temp_bytes));
+    cudaError_t e = cub::DeviceRadixSort::SortKeys(scratch, temp_bytes, (const uint32_t *)list, tmp, (int)n, 0, key_bits, st);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpyAsync(list, tmp, (size_t)n * 4, cudaMemcpyDeviceToDevice, st);
+}
+
 }  // namespace tad
