@@ -1094,6 +1094,8 @@ int tad_init(const tad_config *cfg, tad_ctx **out)
     ok = ok && cudaEventCreateWithFlags(&ctx->start_ev, cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; ok && i <= kMaxXChunks; i++) ok = cudaEventCreateWithFlags(&ctx->x_ev[i], cudaEventDisableTiming) == cudaSuccess;
     if (const char *e = getenv("TAD_OPTIMISTIC")) ctx->optimistic = atoi(e);
+    // default: the faster measured path per world size: peer pull up to 4 ranks, NCCL exchange at 8
+    ctx->peer_pull = cfg->world_size <= 4 ? 1 : 0;
     if (const char *e = getenv("TAD_PEER_PULL")) ctx->peer_pull = atoi(e);
     if (const char *e = getenv("TAD_EXACT_PULL")) ctx->exact_pull = atoi(e);
     if (const char *e = getenv("TAD_SORT_CLASSES")) ctx->sort_classes = atoi(e);
