@@ -64,18 +64,14 @@ def kalman_loglike(y, phi, theta, sigma2, want_forecast=False):
         F = p00 + 2.0 * p01 + p11
         if not (F > 0.0) or not math.isfinite(F):
             return (-1e300, 0.0) if want_forecast else -1e300
-        # statsmodels' univariate inverse (_kalman_filter.pyx.in: _inverse_univariate): ONE reciprocal of F, then
-        # tmp2 = F^-1 v and tmp3 = F^-1 Z; the update uses P Z' tmp2 and P - (P Z')(tmp3 P)
-        inv = 1.0 / F
-        g = inv * v
         if t >= 1:
-            ll += -0.5 * (LOG_2PI + math.log(F) + v * g)
+            ll += -0.5 * (LOG_2PI + math.log(F) + v * v / F)
         # P Z' and the filtered moments
         z0, z1, z2 = p00 + p01, p01 + p11, p02 + p12
-        w0, w1, w2 = inv * z0, inv * z1, inv * z2
+        g = v / F
         f0, f1, f2 = a0 + z0 * g, a1 + z1 * g, a2 + z2 * g
-        c00, c01, c02 = p00 - z0 * w0, p01 - z0 * w1, p02 - z0 * w2
-        c11, c12, c22 = p11 - z1 * w1, p12 - z1 * w2, p22 - z2 * w2
+        c00, c01, c02 = p00 - z0 * z0 / F, p01 - z0 * z1 / F, p02 - z0 * z2 / F
+        c11, c12, c22 = p11 - z1 * z1 / F, p12 - z1 * z2 / F, p22 - z2 * z2 / F
         # prediction: a = T f ; P = T C T' + R Q R'
         a0, a1, a2 = f0 + f1, phi * f1 + f2, 0.0
         p00 = c00 + 2.0 * c01 + c11

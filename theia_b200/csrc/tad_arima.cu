@@ -180,16 +180,12 @@ __host__ __device__ __forceinline__ void kalman_step(Kalman &k, double yt, bool 
     const double v = yt - (k.a0 + k.a1);
     const double F = k.p00 + 2.0 * k.p01 + k.p11;
     if (!(F > 0.0) || !isfinite(F)) { k.dead = true; return; }
-    // statsmodels' univariate inverse (_kalman_filter.pyx.in, _inverse_univariate): ONE reciprocal of F, then tmp2 = F^-1 v and
-    // tmp3 = F^-1 Z; the update uses P Z' tmp2 and P - (P Z')(tmp3 P).  Same operation order as oracle/arima_oracle.py.
-    const double inv = 1.0 / F;
-    const double g = inv * v;
-    if (count) k.ll += -0.5 * (kLog2Pi + log(F) + v * g);
+    if (count) k.ll += -0.5 * (kLog2Pi + log(F) + v * v / F);
     const double z0 = k.p00 + k.p01, z1 = k.p01 + k.p11, z2 = k.p02 + k.p12;
-    const double w0 = inv * z0, w1 = inv * z1, w2 = inv * z2;
+    const double g = v / F;
     const double f0 = k.a0 + z0 * g, f1 = k.a1 + z1 * g, f2 = k.a2 + z2 * g;
-    const double c00 = k.p00 - z0 * w0, c01 = k.p01 - z0 * w1, c02 = k.p02 - z0 * w2;
-    const double c11 = k.p11 - z1 * w1, c12 = k.p12 - z1 * w2, c22 = k.p22 - z2 * w2;
+    const double c00 = k.p00 - z0 * z0 / F, c01 = k.p01 - z0 * z1 / F, c02 = k.p02 - z0 * z2 / F;
+    const double c11 = k.p11 - z1 * z1 / F, c12 = k.p12 - z1 * z2 / F, c22 = k.p22 - z2 * z2 / F;
     k.a0 = f0 + f1; k.a1 = k.phi * f1 + f2; k.a2 = 0.0;
     k.p00 = c00 + 2.0 * c01 + c11;
     k.p01 = k.phi * (c01 + c11) + c02 + c12;
