@@ -100,6 +100,10 @@ def main():
         got, st = eng.run(mine, algo="EWMA", tad_id="multi", emit_all=True, global_rows=len(table["value"]))
         assert st["phase_ms"]["hist"] > 0.0
         np.savez(os.path.join(out_dir, "res_nccl_EWMA_%d.npz" % rank), **got)
+        table = case_table("skewed")                                       # the NCCL exchange with the spill path behind it
+        mine = sharding.shard_rows(table, rank, world)
+        got, st = eng.run(mine, algo="EWMA", tad_id="multi", emit_all=True, global_rows=len(table["value"]))
+        np.savez(os.path.join(out_dir, "res_ncclskew_EWMA_%d.npz" % rank), **got)
         eng.close()
     dist.barrier()
     dist.destroy_process_group()

@@ -48,8 +48,8 @@ def test_ranks_on_gpus_match_the_oracle(tmp_path, world):
     from tests.util import assert_same_rows, oracle_rows
     _launch("gpu", world, tmp_path, 29620 + world)
     for name, algos in (("spread", ("EWMA", "DBSCAN")), ("skewed", ("EWMA", "DBSCAN")), ("xpull", ("EWMA", "DBSCAN")),
-                        ("nccl", ("EWMA",))):
-        table = case_table({"nccl": "spread", "xpull": "skewed"}.get(name, name))
+                        ("nccl", ("EWMA",)), ("ncclskew", ("EWMA",))):
+        table = case_table({"nccl": "spread", "xpull": "skewed", "ncclskew": "skewed"}.get(name, name))
         for algo in algos:
             parts = [np.load(os.path.join(tmp_path, "res_%s_%s_%d.npz" % (name, algo, r))) for r in range(world)]
             got = {k: np.concatenate([p[k] for p in parts]) for k in parts[0].files}

@@ -277,7 +277,9 @@ int pick_logb(const tad_ctx *ctx, uint64_t rows)
 {
     if (ctx->debug_logb >= 0) return ctx->debug_logb;
     // mean bucket ~ 0.375 * capacity: connection sizes are lumpy, so leave head-room
-    uint64_t target = (uint64_t)kGroupTarget;
+    // 8 ranks: twice the rows per bucket -- half as many, twice as large pieces for the peer pull (N = 8: group phase 6.3 -> 5.0 ms,
+    // profiles/r02/ab8_summary.txt); every rank derives the same value from the same world size
+    uint64_t target = (uint64_t)kGroupTarget * (ctx->cfg.world_size >= 8 ? 2 : 1);
     if (ctx->debug_target > 0) target = (uint64_t)ctx->debug_target;
     int logb = 0;
     while (logb < 22 && (rows >> logb) > target) logb++;
@@ -1094,8 +1096,11 @@ int tad_init(const tad_config *cfg, tad_ctx **out)
     ok = ok && cudaEventCreateWithFlags(&ctx->start_ev, cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; ok && i <= kMaxXChunks; i++) ok = cudaEventCreateWithFlags(&ctx->x_ev[i], cudaEventDisableTiming) == cudaSuccess;
     if (const char *e = getenv("TAD_OPTIMISTIC")) ctx->optimistic = atoi(e);
-    // default: the faster measured path per world size: peer pull up to 4 ranks, NCCL exchange at 8
-    ctx->peer_pull = cfg->world_size <= 4 ? 1 : 0;
+    // defaults = the fastest measured configuration per world size: peer pull everywhere, the exact fallback
+    // pulled as well, capacity-class lists sorted by bucket from 4 ranks on (locality of the small remote reads)
+    ctx->peer_pull = 1;
+    ctx->exact_pull = 1;
+    ctx->sort_classes = cfg->world_size >= 4 ? 1 : 0;
     if (const char *e = getenv("TAD_PEER_PULL")) ctx->peer_pull = atoi(e);
     if (const char *e = getenv("TAD_EXACT_PULL")) ctx->exact_pull = atoi(e);
     if (const char *e = getenv("TAD_SORT_CLASSES")) ctx->sort_classes = atoi(e);
