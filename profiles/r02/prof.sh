@@ -12,4 +12,8 @@ tail -2 gpurun_out/r02_full.log
 ncu -i gpurun_out/r02_full.ncu-rep --page raw --csv > gpurun_out/r02_full_raw.csv 2> /dev/null
 ls -la gpurun_out/r02_full.ncu-rep gpurun_out/r02_full_raw.csv
 SECONDS=0
+timeout 600 python -m pytest tests -m gpu -x -q -s > gpurun_out/r02_gpu_tests.log 2>&1; echo "rc=$? after $SECONDS s" >> gpurun_out/r02_gpu_tests.log
+grep -h "ARIMA vs\|passed\|failed\|rc=" gpurun_out/r02_gpu_tests.log | tail -8
+timeout 120 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/r02_smoke.log 2>&1; tail -2 gpurun_out/r02_smoke.log
+SECONDS=0
 timeout 900 python bench.py > gpurun_out/r02_bench_line.json 2> gpurun_out/r02_bench_line.err; echo "bench: $SECONDS s"; tail -c 400 gpurun_out/r02_bench_line.json
