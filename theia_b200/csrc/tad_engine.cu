@@ -277,9 +277,10 @@ int pick_logb(const tad_ctx *ctx, uint64_t rows)
 {
     if (ctx->debug_logb >= 0) return ctx->debug_logb;
     // mean bucket ~ 0.375 * capacity: connection sizes are lumpy, so leave head-room
-    // 8 ranks: twice the rows per bucket -- half as many, twice as large pieces for the peer pull (N = 8: group phase 6.3 -> 5.0 ms,
-    // profiles/r02/ab8_summary.txt); every rank derives the same value from the same world size
-    uint64_t target = (uint64_t)kGroupTarget * (ctx->cfg.world_size >= 8 ? 2 : 1);
+    // 4 ranks and more: twice the rows per bucket -- half as many, twice as large pieces for the peer pull (group phase at N = 8:
+    // 6.3 -> 5.0 ms, at N = 4: 4.4 -> 4.2 ms; profiles/r02/ab8_summary.txt, ab9_summary.txt); every rank derives the same value
+    // from the same world size
+    uint64_t target = (uint64_t)kGroupTarget * (ctx->cfg.world_size >= 4 ? 2 : 1);
     if (ctx->debug_target > 0) target = (uint64_t)ctx->debug_target;
     int logb = 0;
     while (logb < 22 && (rows >> logb) > target) logb++;

@@ -39,7 +39,7 @@ def key_hash(table: dict) -> np.ndarray:
 
 
 def pick_logb(total_rows: int, world: int = 1) -> int:
-    target = GROUP_TARGET * (2 if world >= 8 else 1)      # tad_engine.cu: pick_logb
+    target = GROUP_TARGET * (2 if world >= 4 else 1)      # tad_engine.cu: pick_logb
     logb = 0
     while logb < 22 and (total_rows >> logb) > target:
         logb += 1
