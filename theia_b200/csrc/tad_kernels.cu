@@ -1131,13 +1131,18 @@ __global__ void __launch_bounds__(NT, 5) detect_ewma_direct_kernel(const SeriesE
         // ---- pass 1: stddev_samp (Welford in time order; see series_stddev for the exact-division argument) ---------
         double cnt = 0.0, avg = 0.0, m2 = 0.0;
         Sector4 cur = ldg_sector(vs);
+        // reciprocals of the counts, fetched ONE SECTOR AHEAD: the table load is then never on the Welford chain (in the first
+        // capture of this kernel 25 % of the stall samples sat on q0 = d * rc[j] waiting for it, profiles/r02_source_lines_detect.txt)
+        double rn[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) rn[j] = g_rcp[min((uint32_t)max(j + 1 - mis, 0), kRcpTable)];
         for (uint32_t g = 0; g < ng; g++) {
             Sector4 nxt = cur;
             if (g + 1 < ng) nxt = ldg_sector(vs + 4 * (g + 1));
             const int i0 = (int)(4 * g) - mis;                    // element index of the sector's first value
-            double rc[4];
+            const double rc[4] = {rn[0], rn[1], rn[2], rn[3]};
 #pragma unroll
-            for (int j = 0; j < 4; j++) rc[j] = g_rcp[min((uint32_t)max(i0 + j + 1, 0), kRcpTable)];
+            for (int j = 0; j < 4; j++) rn[j] = g_rcp[min((uint32_t)max(i0 + 4 + j + 1, 0), kRcpTable)];
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 const int idx = i0 + j;
