@@ -572,6 +572,9 @@ def run_ours(args):
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic(dom, rows), "peak_source": peak_src,
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full "
+                                           "capture of the shipped build (profiles/r02_traffic.json, valid for the 1e8-row workload); "
+                                           "ncu cannot run inside the timed bench",
                          "note": "achieved = algorithmic bytes (29 B/row; hist 17) / CUDA-event time of the phase; the group phase is "
                                  "three launches of one kernel template (capacity classes)",
                          "pipeline_frac": rows * BYTES_PER_ROW / (ms_dev * 1e-3) / 1e9 / peak},
