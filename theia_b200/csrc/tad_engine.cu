@@ -189,6 +189,7 @@ struct tad_ctx {
     DevBuf xbuf;                                    // exported: [counters: B x u32, padded][slots: B x slot x Row32]
     void *peer_x[kMaxRanks]{};                      // peers' xbuf mapped into this process
     bool peers_mapped = false;
+    size_t x_agreed = 0;                            // exported size all ranks agreed on at the last (re)mapping
     DevBuf xcnt, xtotal;                            // per-source counts / totals of the owned bucket range
 };
 
@@ -563,7 +564,9 @@ void run_job(tad_ctx *ctx, tad_job *job)
     // regrow together: unmap, barrier (nobody maps a buffer that is about to be freed), reallocate, exchange the IPC
     // handles, map.  First job or a larger table only.
     auto ensure_exported = [&](size_t need) {
-        if (need <= ctx->xbuf.cap && ctx->peers_mapped) return;
+        // the decision must be the same on every rank: it is taken on the size the ranks last agreed on, not on the local
+        // capacity (which may differ when one rank's allocation fell back to the exact size under memory pressure)
+        if (need <= ctx->x_agreed && ctx->peers_mapped) return;
         static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
         for (int r = 0; r < world; r++)
             if (ctx->peer_x[r]) { CU(cudaIpcCloseMemHandle(ctx->peer_x[r])); ctx->peer_x[r] = nullptr; }
@@ -591,6 +594,7 @@ void run_job(tad_ctx *ctx, tad_job *job)
             }
         }
         ctx->peers_mapped = true;
+        ctx->x_agreed = need;
     };
     // ---- several GPUs, optimistic partition + peer pull ---------------------------------------------------------------
     // Every rank scatters its rows into fixed-capacity slots of ALL global buckets (slot = kGroupCap / world rows: a
