@@ -33,7 +33,7 @@ class _Result(C.Structure):
 
 
 def build(force: bool = False) -> str:
-    srcs = [os.path.join(HERE, f) for f in ("tad_oracle.c", "arima_oracle.c", "Makefile")]
+    srcs = [os.path.join(HERE, f) for f in ("tad_oracle.c", "Makefile")]
     if (force or not os.path.exists(LIB_PATH)
             or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)):
         subprocess.check_call(["make", "-s", "-C", HERE])

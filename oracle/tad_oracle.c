@@ -187,7 +187,7 @@ static void do_series(const prow *rows, uint32_t n, const oracle_spec *sp, outve
         for (uint32_t i = 0; i < n; i++) calc[i] = 0.0;     /* :312-322 */
         dbscan_flags(x, n, flag, tmp, pc);
     } else {
-        return;                                             /* ARIMA: oracle/arima_oracle.c */
+        return;                                             /* ARIMA: oracle/arima_oracle.py */
     }
     for (uint32_t i = 0; i < n; i++)
         if (sp->emit_all || flag[i]) out_push(o, &rows[0], rows[i].t, sd, calc[i], x[i], flag[i]);
@@ -361,3 +361,7 @@ void tad_oracle_dbscan(const uint64_t *v, uint32_t n, uint8_t *flag)
     dbscan_flags(x, n, flag, tmp, pc);
     free(x); free(tmp); free(pc);
 }
+
+/* ARIMA has no C port: the authoritative ARIMA oracle is oracle/arima_oracle.py (SciPy's own L-BFGS-B and Brent, the routines
+ * statsmodels itself calls); tad_oracle_run() returns no rows for algo = ARIMA.  Callers ask here before they rely on it. */
+int tad_oracle_arima_available(void) { return 0; }
