@@ -223,3 +223,26 @@ def test_dictionary_matches_a_python_dict_on_many_values():
             want[v] = len(order)
             order.append(v)
     assert names == order and ids.tolist() == [want[v] for v in vals]
+
+
+def test_stream_reader_equals_whole_body_reader_for_any_split():
+    """read_blocks_stream decodes a Native stream that arrives in arbitrary pieces (down to single bytes) into exactly the table
+    the whole-body reader gives, and a stream that ends inside a block is an error."""
+    import random
+    flows = _named_flows(seed=3, series=30, points=25)
+    stream = _flows_as_native(flows, block_rows=97)
+    whole = chn.flows_from_native(stream)
+    rng = random.Random(1)
+    for _ in range(20):
+        cuts = sorted(rng.sample(range(1, len(stream)), rng.randint(1, 30)))
+        pieces = [stream[a:b] for a, b in zip([0] + cuts, cuts + [len(stream)])]
+        got = chn.flows_from_native(iter(pieces))
+        assert set(got) == set(whole)
+        for k in whole:
+            assert np.array_equal(np.asarray(got[k]), np.asarray(whole[k])), k
+    got = chn.flows_from_native(stream[i:i + 1] for i in range(len(stream)))
+    assert all(np.array_equal(np.asarray(got[k]), np.asarray(whole[k])) for k in whole)
+    assert chn.flows_from_native(iter([])) == {}
+    import pytest
+    with pytest.raises(ValueError):
+        chn.flows_from_native(iter([stream[:-5]]))

@@ -304,3 +304,63 @@ def test_null_stddev_goes_into_the_block_as_the_column_default():
     a = chn.read_native(chn.tadetector_block_from_result(got, plan, dicts, "DBSCAN", "t"))
     b = chn.read_native(chn.tadetector_block(ad._result_rows(got, plan, dicts, "DBSCAN", "t", None)))
     assert a["throughputStandardDeviation"].tolist() == [0.0, 2.5] == b["throughputStandardDeviation"].tolist()
+
+
+def test_streamed_select_is_decoded_block_by_block_and_mid_stream_errors_surface():
+    """The job entry reads `SELECT ... FORMAT Native` through ClickHouseHTTP.select_native_stream: pieces of the body are
+    decoded into blocks as they arrive (same table as decoding the whole body), main() produces the same INSERT as with the
+    buffered transport, and ClickHouse's `Code: N. DB::Exception` trailer of a broken stream is raised as ClickHouseError."""
+    from . import test_host_mirror as thm
+    from .test_host_mirror_on_oracle import OracleEngine
+    fl = thm._flows(seed=4)
+    types = dict(chn_types(fl))
+    cols = [(k, types[k], np.asarray(v).astype(np.uint32) if types[k] == "String" and np.asarray(v).dtype.kind in "iu" else v)
+            for k, v in fl.items()]
+    n = len(fl["throughput"])
+    stream = b"".join(chn.write_native([(k, t, v[lo:lo + 700]) for k, t, v in cols]) for lo in range(0, n, 700))
+    state = {"fail": False}
+
+    class H(http.server.BaseHTTPRequestHandler):
+        def do_POST(self):
+            self.rfile.read(int(self.headers.get("Content-Length", 0)))
+            q = urllib.parse.parse_qs(urllib.parse.urlparse(self.path).query)["query"][0]
+            if q.startswith("INSERT"):
+                H.inserted = True
+                self.send_response(200); self.send_header("Content-Length", "0"); self.end_headers()
+                return
+            assert "wait_end_of_query" not in self.path            # the streamed SELECT must not make the server buffer the result
+            body = stream if not state["fail"] else stream[: len(stream) // 2] + b"Code: 241. DB::Exception: Memory limit (total) exceeded"
+            self.send_response(200)
+            self.send_header("Content-Length", str(len(body)))
+            self.end_headers()
+            for i in range(0, len(body), 4096):                      # many small writes: blocks straddle the pieces
+                self.wfile.write(body[i:i + 4096])
+
+        def log_message(self, *a):
+            pass
+
+    srv = http.server.HTTPServer(("127.0.0.1", 0), H)
+    threading.Thread(target=srv.serve_forever, daemon=True).start()
+    try:
+        ch = ad.ClickHouseHTTP("jdbc:clickhouse://127.0.0.1:%d" % srv.server_address[1])
+        got = chn.flows_from_native(ch.select_native_stream("SELECT 1", piece=1500))
+        want = chn.flows_from_native(stream)
+        assert set(got) == set(want) and all(np.array_equal(np.asarray(got[k]), np.asarray(want[k])) for k in want)
+        # main() over the streaming transport == main() over the buffered fake transport
+        class Rec(ad.ClickHouseHTTP):
+            def insert_native(self, table, block):
+                self.block = block
+        tr = Rec("jdbc:clickhouse://127.0.0.1:%d" % srv.server_address[1])
+        assert ad.main(["--algo", "EWMA", "--id", "s1", "--agg-flow", "svc"], engine=OracleEngine(), transport=tr) == 0
+        tr2 = _FakeTransport(stream)
+        assert ad.main(["--algo", "EWMA", "--id", "s1", "--agg-flow", "svc"], engine=OracleEngine(), transport=tr2) == 0
+        a, b = chn.read_native(tr.block), chn.read_native(tr2.inserts[0][1])
+        assert len(a["id"]) == len(b["id"]) > 1
+        key = lambda d: sorted(zip(d["destinationServicePortName"].tolist(), d["flowEndSeconds"].tolist(), d["algoCalc"].tolist()))
+        assert key(a) == key(b)
+        state["fail"] = True
+        with pytest.raises(ad.ClickHouseError) as ei:
+            chn.flows_from_native(ch.select_native_stream("SELECT 1", piece=1500))
+        assert ei.value.code == 241 and "Memory limit" in ei.value.text
+    finally:
+        srv.shutdown()

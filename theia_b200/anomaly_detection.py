@@ -28,6 +28,7 @@ import getopt
 import json
 import logging
 import os
+import re
 import sys
 import time
 import uuid
@@ -515,6 +516,39 @@ class ClickHouseHTTP:
     def select_native(self, sql: str) -> bytes:
         return self._post(sql.rstrip() + " FORMAT Native")
 
+    def select_native_stream(self, sql: str, piece: int = 4 << 20):
+        """The same SELECT as a generator of byte pieces, decoded block by block by the caller while the rest is still on the
+        wire.  No ``wait_end_of_query`` here (it would make the server buffer a multi-gigabyte result before the first byte):
+        a failure before the first block shows in the status / exception header, one in mid-stream as ClickHouse's
+        ``Code: N. DB::Exception: ...`` text at the end of the body, which is raised as :class:`ClickHouseError`."""
+        import urllib.parse
+        import urllib.request
+        params = {"query": sql.rstrip() + " FORMAT Native"}
+        if self.database:
+            params["database"] = self.database
+        req = urllib.request.Request(self.base + "?" + urllib.parse.urlencode(params), data=b"", method="POST")
+        if self.user:
+            req.add_header("X-ClickHouse-User", self.user)
+        if self.password:
+            req.add_header("X-ClickHouse-Key", self.password)
+        with urllib.request.urlopen(req, timeout=self.timeout) as resp:
+            code = resp.headers.get("X-ClickHouse-Exception-Code")
+            if code not in (None, "", "0"):
+                raise ClickHouseError(int(code), resp.read(2000).decode(errors="replace"))
+            tail = b""
+            while True:
+                b = resp.read(piece)
+                if not b:
+                    break
+                tail = (tail + b)[-600:]
+                yield b
+            i = tail.rfind(b"DB::Exception")
+            if i >= 0:
+                j = tail.rfind(b"Code:", 0, i)
+                text = tail[j if j >= 0 else i:].decode(errors="replace")
+                m = re.search(r"Code:\s*(\d+)", text)
+                raise ClickHouseError(int(m.group(1)) if m else -1, text)
+
     def insert_native(self, table: str, block: bytes) -> None:
         self._post("INSERT INTO %s FORMAT Native" % table, block)
 
@@ -579,15 +613,18 @@ def main(argv=None, engine=None, transport=None) -> int:
                           a["svc_port_name"], a["pod_name"], a["pod_namespace"])
         pushdown = os.getenv("TAD_IPV4_PUSHDOWN", "0") == "1"
         sql = raw_select_sql(plan, a["pod_label"], a["pod_name"], a["pod_namespace"], ipv4_pushdown=pushdown)
+        def read(q):          # block-by-block while the response arrives when the transport can stream, else the whole body
+            if hasattr(transport, "select_native_stream"):
+                return chn.flows_from_native(transport.select_native_stream(q))
+            return chn.flows_from_native(transport.select_native(q))
         try:
-            stream = transport.select_native(sql)
+            flows = read(sql)
         except Exception as e:
             if not pushdown or not _is_ipv4_pushdown_failure(e):
                 raise
             logger.info("IPv4 push-down failed (non-IPv4 addresses?): reading the addresses as text")
             sql = raw_select_sql(plan, a["pod_label"], a["pod_name"], a["pod_namespace"])
-            stream = transport.select_native(sql)
-        flows = chn.flows_from_native(stream)
+            flows = read(sql)
         for c in (x.split(" AS ")[-1] for x in sql[len("SELECT "):sql.index(" FROM ")].split(", ")):   # empty table: no block at all
             flows.setdefault(c, np.zeros(0, dtype=np.uint64 if c == "throughput" else np.uint32))
         tad_id = a["id"] or str(uuid.uuid4())                               # write_anomaly_detection_result (:715-718)

@@ -161,6 +161,53 @@ def read_blocks(data):
         yield cols, types, rows
 
 
+def _read_one_block(buf, p: int):
+    """One block starting at ``p``: (cols, types, rows, next_p).  Raises ValueError when the buffer ends early."""
+    ncols, p = _varuint(buf, p)
+    rows, p = _varuint(buf, p)
+    if ncols > len(buf) - p or (ncols and rows > len(buf) - p):
+        raise ValueError("truncated Native block (header claims %d columns x %d rows in %d bytes)" % (ncols, rows, len(buf) - p))
+    cols, types = {}, {}
+    for _ in range(ncols):
+        name, p = _string(buf, p)
+        typ, p = _string(buf, p)
+        cols[name], p = _read_data(buf, p, typ, rows)
+        types[name] = typ
+    return cols, types, rows, p
+
+
+def read_blocks_stream(chunks):
+    """Like :func:`read_blocks`, for a Native stream that arrives in pieces (an iterable of bytes objects, e.g. an HTTP body read
+    4 MB at a time): a block is decoded as soon as its last byte is there, and the bytes of finished blocks are dropped, so the
+    peak memory is one block plus one piece instead of the whole response.  The yielded columns own their data (copies; String
+    columns keep a private copy of their block)."""
+    pending = bytearray()
+    it = iter(chunks)
+    eof = False
+    while True:
+        if pending:
+            try:
+                snap = bytes(pending)                      # a stable buffer for the zero-copy views of this attempt
+                cols, types, rows, used = _read_one_block(memoryview(snap), 0)
+            except ValueError:
+                if eof:
+                    raise
+            else:
+                del pending[:used]
+                yield {k: (v if isinstance(v, (StringColumn, tuple)) else np.array(v)) for k, v in cols.items()}, types, rows
+                continue
+        if eof:
+            return
+        try:
+            piece = next(it)
+        except StopIteration:
+            eof = True
+            if not pending:
+                return
+            continue
+        pending += piece
+
+
 def read_native(data) -> dict:
     """All blocks of a Native stream concatenated: ``{column: numpy array}`` (String columns as object arrays --
     use :func:`read_blocks` to keep them as :class:`StringColumn` and avoid materialising Python strings)."""
@@ -184,9 +231,11 @@ def read_native(data) -> dict:
 def flows_from_native(data) -> dict:
     """Native stream of the stage-A select -> the ``flows`` dict :func:`theia_b200.anomaly_detection.anomaly_detection`
     takes.  sourceIP / destinationIP become u32 where every value is a dotted quad (the common case: the engine's key
-    columns are filled without creating a Python string per row); otherwise they stay strings for the dictionary."""
+    columns are filled without creating a Python string per row); otherwise they stay strings for the dictionary.
+    ``data``: the whole stream as bytes, or an iterable of pieces (decoded block by block as they arrive)."""
     parts, order = {}, []
-    for cols, _types, _rows in read_blocks(data):
+    blocks = read_blocks(data) if isinstance(data, (bytes, bytearray, memoryview)) else read_blocks_stream(data)
+    for cols, _types, _rows in blocks:
         for k, v in cols.items():
             if isinstance(v, StringColumn):
                 if k in ("sourceIP", "destinationIP"):
