@@ -76,3 +76,22 @@ def test_sharded_generator_is_balanced_and_spreads_every_connection():
         for p in parts:                                                # a connection's points live on every rank
             k = p["src_ip"].astype(np.uint64) << np.uint64(32) | p["flow_start"].astype(np.uint64)
             assert len(np.unique(k)) == 25 * world
+
+
+def test_committed_round2_line_has_parity_sides_and_a_full_size_cpu_arm():
+    """profiles/r02_bench_line.json: the default `python bench.py` on a B200 at the end of round 2."""
+    d = json.load(open(os.path.join(ROOT, "profiles", "r02_bench_line.json")))
+    assert BASE_KEYS <= set(d) and d["n_gpus"] == 1 and d["warmup"] >= 3 and d["gpu_launches"] > 0
+    assert d["parity"]["ok"] is True and d["parity"]["checked"] >= 2500          # sampled connections, bit-exact vs the oracle
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["traffic"] > 0
+    assert d["e2e"]["h2d_bytes_per_step"] == 29 * d["config"]["rows_per_gpu"] and d["e2e"]["value"] < d["value"]
+    c = d["cpu_baseline"]
+    assert c["kind"] == "port" and c["threads_used"] == c["cores"] > 1 and "100000000 rows" in c["sample"]
+    sides = {s["algo"]: s for s in d["side"]}
+    assert set(sides) == {"DBSCAN", "ARIMA"}
+    assert sides["DBSCAN"]["records"] == 240_000_000 and sides["DBSCAN"]["parity"]["ok"] is True
+    assert sides["ARIMA"]["parity"]["ok"] is True and sides["ARIMA"]["parity"]["flags_identical"] >= 0.99
+    for s in sides.values():
+        assert {"bound", "achieved", "peak", "frac"} <= set(s["roofline"])
+    assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
